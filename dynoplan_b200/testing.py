@@ -1,0 +1,219 @@
+"""Workload construction and parity comparison shared by tests/, smoke() and bench.py.
+
+Nothing here computes expansion results: ``compare_edges`` only compares two result
+sets (the CUDA path's and a checker's) under BASELINE.json's tolerances:
+identical candidate sets/order and accept/reject decisions except for logged cases
+within eps = 1e-6 of the delta bound / bounds / contact boundary; transformed states
+within 1e-5 relative.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from .motions import MotionLibrary
+from .problem import BOX, Obstacle, Problem
+from .robots import QUAD2D, QUAD3D, RobotModel, robot_factory
+
+EPS_BAND = 1e-6  # BASELINE.json north_star: eps of the delta bound / contact boundary
+STATE_RTOL = 1e-5  # "transformed states must agree within 1e-5 relative"
+
+
+@dataclass
+class Case:
+    robot: RobotModel
+    obstacles: List[Obstacle]
+    library: MotionLibrary
+    nodes: np.ndarray
+    goal: np.ndarray
+    radius: float
+    goal_radius: float
+    name: str = ""
+
+
+# environment presets for the synthetic workloads
+WINDOW_ENV = {  # geometry of dynobench/envs/quadrotor_v0/window.yaml
+    "min": [1.0, 0.5, 1.0], "max": [5.0, 5.5, 3.0],
+    "obstacles": [([4, 3, 2], [2, .3, 2]), ([1.1, 3, 1.9], [.2, .3, 1]),
+                  ([2, 3, 2.7], [2, .3, .6]), ([2, 3, 1.2], [2, .3, .4])],
+}
+
+DEFAULT_T = {"unicycle1_v0": (5, 21), "unicycle2_v0": (5, 21), "car1_v0": (5, 51),
+             "quad2d_v0": (11, 101), "acrobot_v0": (6, 76), "quad3d_v0": (11, 101)}
+DEFAULT_DELTA = {"unicycle1_v0": .3, "unicycle2_v0": .4, "car1_v0": .3, "quad2d_v0": .5,
+                 "acrobot_v0": .35, "quad3d_v0": .8}
+
+
+def random_box_env(dim: int, n_obs: int, lo: float, hi: float, seed: int) -> List[Obstacle]:
+    """axis-aligned boxes, centres ~U(bounds), sizes ~U[.1,.5]."""
+    rng = np.random.default_rng(seed)
+    obs = []
+    for _ in range(n_obs):
+        c = rng.uniform(lo, hi, size=3)
+        s = rng.uniform(.1, .5, size=3)
+        if dim == 2:
+            c[2], s[2] = 0.0, 1.0
+        obs.append(Obstacle(BOX, [float(v) for v in c], [float(v) for v in s]))
+    return obs
+
+
+def frontier_nodes(robot: RobotModel, library: MotionLibrary, n_nodes: int, p_lb, p_ub,
+                   seed: int) -> np.ndarray:
+    """Synthetic frontier: orientation / angular rates taken from primitive end states so
+    that the delta pass-rate is realistic, positions ~U(bounds), velocities ~U[-1,1]."""
+    rng = np.random.default_rng(seed)
+    off = library.state_off
+    pick = rng.integers(0, library.N, size=n_nodes)
+    nodes = library.states[off[pick + 1] - 1].copy()
+    ti = robot.translation_invariance
+    if ti:
+        nodes[:, :ti] = rng.uniform(np.asarray(p_lb) + .3, np.asarray(p_ub) - .3, size=(n_nodes, ti))
+    if robot.kind == QUAD3D:
+        nodes[:, 7:10] = rng.uniform(-1, 1, size=(n_nodes, 3))
+    elif robot.kind == QUAD2D:
+        nodes[:, 3:5] = rng.uniform(-1, 1, size=(n_nodes, 2))
+    return np.ascontiguousarray(nodes)
+
+
+def synthetic_case(robot_type: str, n_prims: int, n_nodes: int, seed: int = 0,
+                   n_obs: Optional[int] = None, delta: Optional[float] = None,
+                   alpha: float = .5, device: int = 0, library: Optional[MotionLibrary] = None) -> Case:
+    """Synthetic library (GPU generator) + environment + frontier for one robot type."""
+    from .expander import generate_library
+    dim3 = robot_type.startswith("quad3d")
+    if dim3 and n_obs is None:
+        p_lb, p_ub = WINDOW_ENV["min"], WINDOW_ENV["max"]
+        obstacles = [Obstacle(BOX, [float(v) for v in c], [float(v) for v in s])
+                     for c, s in WINDOW_ENV["obstacles"]]
+    elif dim3:
+        p_lb, p_ub = [-5.0] * 3, [5.0] * 3
+        obstacles = random_box_env(3, n_obs, -5, 5, seed)
+    else:
+        p_lb, p_ub = [0.0, 0.0], [6.0, 6.0]
+        obstacles = random_box_env(2, 5 if n_obs is None else n_obs, 0, 6, seed)
+    robot = robot_factory(robot_type, p_lb, p_ub)
+    if library is None:
+        tmin, tmax = DEFAULT_T[robot_type]
+        library = generate_library(robot, n_prims, tmin, tmax, seed=seed, device=device)
+        if robot.kind == QUAD3D:  # loader normalisation (robots.cpp:3130-3137)
+            q = library.states[:, 3:7]
+            q /= np.sqrt((q * q).sum(axis=1, keepdims=True))
+    nodes = frontier_nodes(robot, library, n_nodes, p_lb, p_ub, seed + 1)
+    goal = nodes[0].copy()
+    d = DEFAULT_DELTA[robot_type] if delta is None else delta
+    return Case(robot, obstacles, library, nodes, goal, float(np.float32(alpha) * np.float32(d)),
+                float(d), name=f"{robot_type}-synthetic")
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def golden_problem(system: str, env: str) -> Problem:
+    return Problem.from_yaml(os.path.join(GOLDEN, "envs", system, env + ".yaml"))
+
+
+@dataclass
+class ParityReport:
+    n_edges: int = 0
+    set_mismatch_rows: int = 0
+    set_mismatch_in_band: int = 0
+    set_mismatch_outside_band: int = 0
+    max_dist_err: float = 0.0
+    status_mismatch: int = 0
+    status_mismatch_in_band: int = 0
+    chosen_mismatch: int = 0
+    chosen_mismatch_in_band: int = 0
+    n_valid: int = 0
+    max_state_rel_err: float = 0.0
+    max_cost_err: float = 0.0
+    max_jump_err: float = 0.0
+    max_h_err: float = 0.0
+    notes: List[str] = field(default_factory=list)
+
+    @property
+    def ok(self) -> bool:
+        return (self.set_mismatch_outside_band == 0
+                and self.status_mismatch == self.status_mismatch_in_band
+                and self.chosen_mismatch == self.chosen_mismatch_in_band
+                and self.max_dist_err <= 1e-12
+                and self.max_state_rel_err <= STATE_RTOL
+                and self.max_cost_err <= 1e-12
+                and self.max_jump_err <= 1e-7 and self.max_h_err <= 1e-7)
+
+    def summary(self) -> str:
+        return (f"edges={self.n_edges} valid={self.n_valid} set_mismatch(out/in band)="
+                f"{self.set_mismatch_outside_band}/{self.set_mismatch_in_band} "
+                f"dist_err={self.max_dist_err:.2e} status_mismatch={self.status_mismatch} "
+                f"(in band {self.status_mismatch_in_band}) chosen_mismatch={self.chosen_mismatch} "
+                f"state_rel_err={self.max_state_rel_err:.2e} cost_err={self.max_cost_err:.2e} "
+                f"jump_err={self.max_jump_err:.2e} h_err={self.max_h_err:.2e} ok={self.ok}"
+                + ("".join("\n  " + n for n in self.notes[:10])))
+
+
+def compare_edges(got, want, robot: RobotModel, radius: Optional[float] = None) -> ParityReport:
+    """Compare the CUDA path's records (``got``: dynoplan_b200.expander.Edges) with a
+    checker's (``want``: same fields + ``band``).  Mismatches are tolerated only inside
+    the eps band and are counted (logged) separately."""
+    rep = ParityReport()
+    B = len(want.row_ptr) - 1
+    same_csr = (np.array_equal(got.row_ptr, want.row_ptr)
+                and np.array_equal(got.prim_idx.astype(np.int64), want.prim_idx.astype(np.int64)))
+    if not same_csr:
+        # candidate sets / order differ: classify per row
+        for b in range(B):
+            g = slice(int(got.row_ptr[b]), int(got.row_ptr[b + 1]))
+            w = slice(int(want.row_ptr[b]), int(want.row_ptr[b + 1]))
+            gi, wi = got.prim_idx[g].astype(np.int64), want.prim_idx[w].astype(np.int64)
+            if np.array_equal(gi, wi):
+                continue
+            rep.set_mismatch_rows += 1
+            gd = dict(zip(gi.tolist(), got.delta_dist[g].tolist()))
+            wd = dict(zip(wi.tolist(), want.delta_dist[w].tolist()))
+            only = set(gd) ^ set(wd)
+            for k in only:
+                dd = gd.get(k, wd.get(k))
+                if radius is not None and abs(dd - radius) < EPS_BAND:
+                    rep.set_mismatch_in_band += 1
+                else:
+                    rep.set_mismatch_outside_band += 1
+                    rep.notes.append(f"row {b}: primitive {k} d={dd!r} in only one candidate set")
+            if not only:
+                # same set, different order: only legal for (near-)equal distances
+                gs, ws = got.delta_dist[g], want.delta_dist[w]
+                if np.max(np.abs(np.sort(gs) - np.sort(ws))) > 1e-12:
+                    rep.set_mismatch_outside_band += 1
+                    rep.notes.append(f"row {b}: candidate order differs")
+                else:
+                    rep.set_mismatch_in_band += 1
+        rep.n_edges = int(want.row_ptr[-1])
+        return rep
+    Cn = int(want.row_ptr[-1])
+    rep.n_edges = Cn
+    if Cn == 0:
+        return rep
+    rep.max_dist_err = float(np.max(np.abs(got.delta_dist - want.delta_dist)))
+    if want.status is None:
+        return rep
+    sm = got.status != want.status
+    rep.status_mismatch = int(sm.sum())
+    rep.status_mismatch_in_band = int((sm & (want.band < EPS_BAND)).sum())
+    for i in np.nonzero(sm & ~(want.band < EPS_BAND))[0][:5]:
+        rep.notes.append(f"edge {i}: status got {got.status[i]} want {want.status[i]} "
+                         f"band {want.band[i]:.3e} prim {want.prim_idx[i]}")
+    both = (got.status == 0) & (want.status == 0)
+    rep.n_valid = int(both.sum())
+    if rep.n_valid:
+        cm = both & (got.chosen_index != want.chosen_index)
+        rep.chosen_mismatch = int(cm.sum())
+        rep.chosen_mismatch_in_band = int((cm & (want.band < EPS_BAND)).sum())
+        same = both & ~cm
+        if same.any():
+            xg, xw = got.x_final[same], want.x_final[same]
+            rep.max_state_rel_err = float(np.max(np.abs(xg - xw) / (1.0 + np.abs(xw))))
+            rep.max_cost_err = float(np.max(np.abs(got.cost_motion[same] - want.cost_motion[same])))
+            rep.max_jump_err = float(np.max(np.abs(got.jump_lbt[same] - want.jump_lbt[same])))
+            rep.max_h_err = float(np.max(np.abs(got.h[same] - want.h[same])))
+    return rep
