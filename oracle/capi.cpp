@@ -42,6 +42,9 @@ void *orc_library_create(int nx, int nu, int64_t N, const int64_t *T,
   l->states.assign(states, states + S * nx);
   l->actions.assign(actions, actions + (S - N) * nu);
   l->cost.assign(cost, cost + N);
+  l->keys.resize((size_t)N * nx);
+  for (int64_t i = 0; i < N; i++)
+    std::memcpy(l->keys.data() + i * nx, l->xs(i), sizeof(double) * nx);
   return l;
 }
 void orc_library_destroy(void *l) { delete (Library *)l; }
@@ -116,8 +119,8 @@ void *orc_expand(void *m_, void *l_, int64_t n_use, int B, const double *nodes,
         break;
       const double *x = nodes + (size_t)b * nx;
       m->canonical_state(x, canonical);
-      nearest_r(*m, *l, n_use, canonical, radius, nb[b]);
-      if (filter_only)
+      nearest_r(*m, *l, n_use, canonical, radius, nb[b], (filter_only & 2) != 0);
+      if (filter_only & 1)
         continue;
       er[b].reserve(nb[b].size());
       for (auto &pr : nb[b])
@@ -144,6 +147,7 @@ void *orc_expand(void *m_, void *l_, int64_t n_use, int B, const double *nodes,
   const int64_t C = res->row_ptr[B];
   res->prim_idx.resize(C);
   res->delta_dist.resize(C);
+  filter_only &= 1;
   if (!filter_only)
     res->edges.resize(C);
   for (int b = 0; b < B; b++) {

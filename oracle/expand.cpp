@@ -126,12 +126,22 @@ EdgeResult check_edge(const Model &m, const Library &lib, int64_t prim,
 // (nigh/impl/near_set.hpp:155-157), sorted ascending (kdtree_batch.hpp:211-217).
 void nearest_r(const Model &m, const Library &lib, int64_t n_use,
                const double *canonical, double radius,
-               std::vector<std::pair<double, int64_t>> &out) {
+               std::vector<std::pair<double, int64_t>> &out, bool fast) {
   out.clear();
-  for (int64_t i = 0; i < n_use; i++) {
-    double dd = m.nigh_distance(canonical, lib.xs(i)); // key = first state
-    if (dd <= radius)
-      out.emplace_back(dd, i);
+  const int nx = lib.nx;
+  const double *keys = lib.keys.data(); // key = first state of the primitive
+  if (fast) {
+    for (int64_t i = 0; i < n_use; i++) {
+      double dd;
+      if (nigh_within_fast(m, canonical, keys + i * nx, radius, &dd))
+        out.emplace_back(dd, i);
+    }
+  } else {
+    for (int64_t i = 0; i < n_use; i++) {
+      double dd = m.nigh_distance(canonical, keys + i * nx);
+      if (dd <= radius)
+        out.emplace_back(dd, i);
+    }
   }
   std::sort(out.begin(), out.end());
 }

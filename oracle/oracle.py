@@ -242,12 +242,12 @@ def transform_primitive(model: OracleModel, olib: OracleLibrary, prim: int, x):
 
 def expand(model: OracleModel, olib: OracleLibrary, nodes, radius: float, goal, goal_radius: float,
            heuristic: int = 0, n_use: Optional[int] = None, n_threads: int = 1,
-           filter_only: bool = False, copy: bool = True):
+           filter_only: bool = False, copy: bool = True, fast_filter: bool = False):
     nodes = _vec(nodes).reshape(-1, model.nx)
     B = nodes.shape[0]
     n_use = olib.mlib.N if n_use is None else min(n_use, olib.mlib.N)
     r = lib().orc_expand(model._h, olib._h, n_use, B, _dp(nodes), radius, _dp(_vec(goal)), goal_radius,
-                         heuristic, n_threads, int(filter_only))
+                         heuristic, n_threads, int(filter_only) | (2 if fast_filter else 0))
     try:
         if lib().orc_expand_err(r):
             raise RuntimeError("oracle: quaternion norm check failed (so3_distance)")
