@@ -158,6 +158,8 @@ def compare_edges(got, want, robot: RobotModel, radius: Optional[float] = None) 
     checker's (``want``: same fields + ``band``).  Mismatches are tolerated only inside
     the eps band and are counted (logged) separately."""
     rep = ParityReport()
+    if hasattr(got, "dense"):
+        got = got.dense()  # per-candidate re-indexing of the compacted [V] arrays
     B = len(want.row_ptr) - 1
     same_csr = (np.array_equal(got.row_ptr, want.row_ptr)
                 and np.array_equal(got.prim_idx.astype(np.int64), want.prim_idx.astype(np.int64)))
