@@ -18,8 +18,9 @@ bounds + collision + goal/cost) over that batch; edge checks per step = B x N.
   cpu_baseline  the CPU oracle (port of the reference's expansion) on a bounded sample
 
 Under torchrun (N > 1) every rank holds its own shard of the library (weak scaling,
-N x 100k primitives in total), expands the same frontier and the per-node candidate lists
-are merged with one NCCL all-gather (dynoplan_b200/sharded.py).
+N x 100k primitives in total), expands the same frontier, and the per-node candidate lists
+are merged over the whole library by a node-sliced NCCL all-to-all + merge kernels
+(dynoplan_b200/sharded.py): rank q ends up with the merged lists of nodes [qB/N, (q+1)B/N).
 """
 from __future__ import annotations
 
@@ -126,6 +127,23 @@ def cpu_sample_size(case, threads: int, target_s: float) -> int:
     return int(min(max(n, probe), case.nodes.shape[0]))
 
 
+def pinned_edges(torch, Bq: int, cap_c: int, cap_v: int, nx: int):
+    """Edges whose arrays are numpy views of pinned host tensors (result download target)."""
+    from dynoplan_b200.expander import Edges
+
+    def pin(n, dt):
+        t = torch.empty(n, dtype=dt, pin_memory=True)
+        pinned_edges.keep.append(t)
+        return t.numpy()
+    return Edges(pin(Bq + 1, torch.int64), pin(cap_c, torch.int32), pin(cap_c, torch.float64),
+                 pin(cap_c, torch.uint8), pin(cap_c, torch.int32), pin(cap_v, torch.int32),
+                 pin(cap_v, torch.float64), pin(cap_v, torch.float64), pin(cap_v, torch.float64),
+                 pin(cap_v * nx, torch.float64).reshape(cap_v, nx))
+
+
+pinned_edges.keep = []
+
+
 def run_reference(args, rank: int, world: int):
     """--impl reference: the reference's CPU expansion (oracle port; the reference cannot be
     compiled in this image -- no Eigen/Boost/FCL/OMPL) on the host cores, same workload."""
@@ -216,13 +234,13 @@ def main():
 
     merger = None
     if world > 1:
-        from dynoplan_b200.sharded import ShardMerger
-        merger = ShardMerger(ex, B, rank, world, prim_offset=rank * N)
+        from dynoplan_b200.sharded import ShardedExpander
+        merger = ShardedExpander(ex, rank, world, prim_offset=rank * N)
 
     def step_resident():
         ex.expand_device(B, d_nodes.data_ptr(), case.radius, d_goal.data_ptr(), case.goal_radius, 0)
         if merger is not None:
-            merger.merge_async()
+            merger.merge_last(B)
 
     def barrier():
         if world > 1:
@@ -265,13 +283,20 @@ def main():
     # --- timed region 2: end to end through the host API ----------------------------------
     e2e_times = []
     got = None
+    pinned_out = None
     for i in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
-        got = ex.expand_host(case.nodes, case.radius, case.goal, case.goal_radius, 0)
-        if merger is not None:
-            merger.merge_async()
-            torch.cuda.synchronize()
+        if merger is None:
+            got = ex.expand_host(case.nodes, case.radius, case.goal, case.goal_radius, 0)
+            n_c, n_v = got.n_edges, got.n_valid
+        else:
+            # host nodes in -> shard expansion -> exchange + merge -> this rank's slice on the host
+            merger.expand(case.nodes, case.radius, case.goal, case.goal_radius, 0)
+            Bq, n_c, n_v = merger._merged
+            if pinned_out is None or pinned_out.prim_idx.shape[0] < n_c or pinned_out.chosen_index.shape[0] < n_v:
+                pinned_out = pinned_edges(torch, Bq, int(n_c * 1.2) + 1024, int(n_v * 1.2) + 1024, nx)
+            merger.fetch(pinned_out)
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             e2e_times.append(dt)
@@ -279,8 +304,10 @@ def main():
     e2e_ms = 1e3 * float(np.mean(e2e_times))
     # [C] arrays: prim_idx, delta_dist, status, valid_slot; [V] arrays: chosen_index, cost_motion,
     # jump_lbt, h, x_final
-    d2h_bytes = int((B + 1) * 8 + got.n_edges * (4 + 8 + 1 + 4) + got.n_valid * (4 + 8 + 8 + 8 + nx * 8))
+    d2h_bytes = int((B + 1) * 8 + n_c * (4 + 8 + 1 + 4) + n_v * (4 + 8 + 8 + 8 + nx * 8))
     h2d_bytes = int(B * nx * 8 + nx * 8)
+    if merger is not None:  # single-GPU records of this rank's shard for the roofline bookkeeping
+        got = ex.expand(case.nodes, case.radius, case.goal, case.goal_radius, 0)
 
     # --- reduce over ranks: max time, summed work -------------------------------------------
     ms_step = ms_total / args.steps
@@ -317,8 +344,8 @@ def main():
                 "status_counts[valid,last_state,bounds,collision]": status_counts,
                 "l2_policy": "inputs larger than L2: primitive store "
                              f"{case.library.states.nbytes / 1e6:.0f} MB fp64 vs 126 MB L2",
-                "parallelism": f"library sharded over {world} GPU(s), all-gather merge" if world > 1
-                               else "single GPU",
+                "parallelism": f"library sharded over {world} GPUs (one {N}-primitive shard each), "
+                               "node-sliced all-to-all merge" if world > 1 else "single GPU",
             },
             "e2e": {"value": e2e_value, "unit": "edge checks/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},

@@ -56,6 +56,13 @@ class MotionLibrary:
         return MotionLibrary(self.nx, self.nu, self.T[:n].copy(), self.states[:S].copy(),
                              self.actions[:S - n].copy(), self.cost[:n].copy())
 
+    def slice(self, a: int, b: int) -> "MotionLibrary":
+        """Primitives [a, b) (one shard of a library split by primitive index)."""
+        off = self.state_off
+        s, e = int(off[a]), int(off[b])
+        return MotionLibrary(self.nx, self.nu, self.T[a:b].copy(), self.states[s:e].copy(),
+                             self.actions[s - a:e - b].copy(), self.cost[a:b].copy())
+
     @staticmethod
     def from_lists(trajs, nx: int, nu: int, cost=None) -> "MotionLibrary":
         T = np.array([len(t[0]) for t in trajs], dtype=np.int64)
