@@ -119,7 +119,7 @@ class ShardedExpander:
         self.ex, self.rank, self.world, self.prim_offset = expander, rank, world, int(prim_offset)
         self.xchg = ShardExchange(rank, world, group)
         self._lib = _abi.lib()
-        self.launches_per_step = 4 + 6  # pack (partial, scan, heavy, light) + merge kernels
+        self.launches_per_step = 4 + 7  # pack (partial, scan, heavy, light) + merge (scan, fill, sort x2, gather, unpack, chosen)
         self._recv = None
         self.slice = (0, 0)
 
