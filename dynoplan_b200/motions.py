@@ -130,7 +130,11 @@ def _read_trajs(path: str):
 
 def load_motion_primitives_new(motions_file: str, robot: RobotModel, max_motions: int = 10 ** 9,
                                add_noise: bool = True, rand: Optional[_LibcRand] = None,
-                               skip_degenerate: bool = False) -> MotionLibrary:
+                               skip_degenerate: bool = False, rand_seed: Optional[int] = None) -> MotionLibrary:
+    """``rand_seed``: ``srand(rand_seed)`` before the noise is drawn.  The reference draws from
+    the process-global ``rand()`` stream wherever it happens to stand (state 1 at the start of
+    a process); pass 1 to get what a fresh reference process loading this file first would
+    get, independent of what else has consumed ``rand()`` in this process."""
     trajs = _read_trajs(motions_file)
     if max_motions < len(trajs):
         trajs = trajs[:max_motions]
@@ -141,16 +145,18 @@ def load_motion_primitives_new(motions_file: str, robot: RobotModel, max_motions
     if any(len(t[0]) < 2 for t in trajs):
         raise RuntimeError("degenerate primitive (fewer than 2 states) in " + motions_file)
     lib = MotionLibrary.from_lists(trajs, robot.nx, robot.nu, cost=[t[2] for t in trajs])
-    finalize_library(lib, robot, add_noise=add_noise, rand=rand)
+    finalize_library(lib, robot, add_noise=add_noise, rand=rand, rand_seed=rand_seed)
     return lib
 
 
 def finalize_library(lib: MotionLibrary, robot: RobotModel, add_noise: bool = True,
-                     rand: Optional[_LibcRand] = None) -> None:
+                     rand: Optional[_LibcRand] = None, rand_seed: Optional[int] = None) -> None:
     """Noise, quaternion normalisation and default cost, in place."""
     off = lib.state_off
     if add_noise:
         rand = rand or _LibcRand()
+        if rand_seed is not None:
+            rand.srand(rand_seed)
         noise = 1e-7
         for i in range(lib.N):
             first, last = int(off[i]), int(off[i + 1]) - 1

@@ -127,7 +127,7 @@ def make_expand_fixtures():
     for system, env in cases.items():
         p = Problem.from_yaml(os.path.join(HERE, "envs", system, env + ".yaml"))
         robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
-        lib = load_motion_primitives_new(os.path.join(HERE, "motions", system + ".msgpack"), robot)
+        lib = load_motion_primitives_new(os.path.join(HERE, "motions", system + ".msgpack"), robot, rand_seed=1)
         delta = testing.DEFAULT_DELTA[p.robotType]
         radius = float(np.float32(.5) * np.float32(delta))
         lo = p.p_lb if robot.translation_invariance else [0, 0]

@@ -29,7 +29,7 @@ CASES = [("unicycle1_v0", "bugtrap_0"), ("unicycle1_v0", "parallelpark_0"),
 def _setup(golden_dir, system, env, n_prims):
     p = testing.golden_problem(system, env)
     robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
-    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot, n_prims)
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot, n_prims, rand_seed=1)
     return p, robot, lib
 
 
@@ -70,23 +70,40 @@ def test_gpu_dbastar_reproduces_reference_and_oracle(oracle, golden_dir, system,
 
 
 def test_gpu_dbastar_quadrotor_and_acrobot(oracle, golden_dir):
-    # systems without a stored reference db solution: oracle parity only
-    for system, env, n_prims, delta, lbf in (("quadrotor_v0", "empty_0", 2000, .8, 30),
-                                             ("acrobot_v0", "swing_up_empty", 1500, .35, 20)):
-        p, robot, lib = _setup(golden_dir, system, env, n_prims)
+    # systems whose shipped fixture libraries are too small to search with: synthetic
+    # libraries (GPU generator), oracle parity of the whole search for a bounded number of
+    # expansions (solved or not: the returned plan leads to the node closest to the goal)
+    from dynoplan_b200.expander import generate_library
+    from dynoplan_b200.problem import BOX, Obstacle
+    for system, env, rtype, n_prims, delta, lbf in (("quadrotor_v0", "empty_0_easy", "quad3d_v0", 20000, .8, 30),
+                                                    ("acrobot_v0", "swing_up_empty", "acrobot_v0", 6000, .35, 20)):
+        p = testing.golden_problem(system, env)
+        if rtype == "quad3d_v0":  # roomier than the shipped instance: random primitives need space
+            p.p_lb, p.p_ub = [-4.0, -4.0, -4.0], [4.0, 4.0, 4.0]
+            p.obstacles = [Obstacle(BOX, [1.0, .5, .3], [.4, 2.0, 2.0]), Obstacle(BOX, [-1.0, -1.0, 0.0], [.5, .5, 3.0])]
+            p.start = [0.0] * 3 + [0, 0, 0, 1.0] + [0.0] * 6
+            p.goal = [2.0, 1.0, .5] + [0, 0, 0, 1.0] + [0.0] * 6
+        robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+        tmin, tmax = testing.DEFAULT_T[rtype]
+        lib = generate_library(robot, n_prims, tmin, tmax, seed=21)
+        if rtype == "quad3d_v0":
+            q = lib.states[:, 3:7]
+            q /= np.sqrt((q * q).sum(axis=1, keepdims=True))
+        kw = dict(delta=delta, max_motions=n_prims, max_expands=400, limit_branching_factor=lbf,
+                  search_timelimit=300e3)
         with GpuExpander(robot, p.obstacles, lib) as ex:
-            got = dbastar(ex, lib, p.start, p.goal,
-                          Options_dbastar(fix_seed=True, delta=delta, max_motions=n_prims, max_expands=3000,
-                                          limit_branching_factor=lbf, search_timelimit=120e3))
+            got = dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, **kw))
         m = oracle.OracleModel(robot, p.obstacles)
-        want = oracle.dbastar(m, oracle.OracleLibrary(lib), p.start, p.goal, delta=delta, max_motions=n_prims,
-                              max_expands=3000, limit_branching_factor=lbf, search_timelimit=120e3)
+        want = oracle.dbastar(m, oracle.OracleLibrary(lib), p.start, p.goal, **kw)
         s = want.summary
-        print(system, env, got.data["terminate_status"], got.data["expands"], s["expands"], got.cost, s["cost"])
+        print(system, env, got.data["terminate_status"], got.data["expands"], s["expands"], got.data["all_nodes"],
+              s["n_nodes"], got.cost, s["cost"])
         assert got.solved == bool(s["solved"])
         assert int(got.data["expands"]) == s["expands"] and int(got.data["all_nodes"]) == s["n_nodes"]
+        assert int(got.data["all_nodes"]) > (20 if rtype == "quad3d_v0" else 0)
         assert np.array_equal(got.motions_used, want.motions_used)
         assert abs(got.cost - s["cost"]) < 1e-4
+        assert np.max(np.abs(got.states - want.states) / (1 + np.abs(want.states))) < 1e-5
 
 
 def test_gpu_dbastar_options_and_termination(golden_dir):

@@ -22,7 +22,7 @@ def _golden(golden_dir, system):
     g = np.load(os.path.join(golden_dir, f"expand_{system}.npz"))
     p = testing.golden_problem(system, str(g["env"]))
     robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
-    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot)
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot, rand_seed=1)
     return g, p, robot, lib
 
 

@@ -77,7 +77,7 @@ def _gloo_worker(rank, world, port, system, n_nodes, ret):
         g = np.load(os.path.join(golden, f"expand_{system}.npz"))
         p = testing.golden_problem(system, str(g["env"]))
         robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
-        lib = load_motion_primitives_new(os.path.join(golden, "motions", system + ".msgpack"), robot)
+        lib = load_motion_primitives_new(os.path.join(golden, "motions", system + ".msgpack"), robot, rand_seed=1)
         nodes = g["nodes"][:n_nodes]
         B, nx = nodes.shape[0], robot.nx
         radius, goal, goal_radius = float(g["radius"]), g["goal"], float(g["goal_radius"])
