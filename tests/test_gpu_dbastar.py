@@ -61,7 +61,7 @@ def test_gpu_dbastar_reproduces_reference_and_oracle(oracle, golden_dir, system,
     assert abs(got.cost - ref["cost"]) < 1e-4
     rs = np.array(ref["states"], dtype=float)
     assert np.max(np.abs(got.states - rs)) < 1e-5 * (1 + np.abs(rs).max())
-    assert abs(float(got.data["goal_distance"]) - ref["goal_distance"]) < 2e-6
+    assert abs(float(got.data["goal_distance"]) - ref["goal_distance"]) < 6e-6  # 6 printed digits
     # speculation is invisible: one node per GPU call gives the same search
     assert int(got1.data["expands"]) == s["expands"] and np.array_equal(got1.motions_used, got.motions_used)
     assert np.array_equal(got1.states, got.states)
