@@ -58,7 +58,7 @@ def test_cuda_matches_oracle_on_synthetic_library(oracle, robot_type):
     rep = testing.compare_edges(got, want, case.robot, case.radius)
     print(robot_type, rep.summary(), t)
     assert rep.ok, rep.summary()
-    assert rep.n_edges > 0 and t["launches"] == 6
+    assert rep.n_edges > 0 and t["launches"] == 10
     counts = np.bincount(got.status, minlength=4)
     print(robot_type, "status counts", counts.tolist())
 
