@@ -130,7 +130,7 @@ class ShardedExpander:
         self._lib = _abi.lib()
         self.mailbox = False
         # nccl: pack (partial, scan, heavy, light) + merge (scan, fill, sort x2, gather, unpack, chosen)
-        self.launches_per_step = 4 + 7
+        self.launches_per_step = 4 + 9
         self._recv = None
         self._bar = None
         self._merged = None
@@ -152,7 +152,7 @@ class ShardedExpander:
             self._bar = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
             dist.barrier(group=self.group)
         self.mailbox = True
-        self.launches_per_step = 6  # merge: scan, fill, sort x2, gather, unpack (dispatch is fused)
+        self.launches_per_step = 8  # merge: scan, fill, sort x4, gather, unpack (dispatch is fused)
 
     def _barrier(self):
         if self.world > 1:

@@ -58,7 +58,7 @@ def test_cuda_matches_oracle_on_synthetic_library(oracle, robot_type):
     rep = testing.compare_edges(got, want, case.robot, case.radius)
     print(robot_type, rep.summary(), t)
     assert rep.ok, rep.summary()
-    assert rep.n_edges > 0 and t["launches"] == 10
+    assert rep.n_edges > 0 and t["launches"] == 12
     counts = np.bincount(got.status, minlength=4)
     print(robot_type, "status counts", counts.tolist())
 
@@ -181,6 +181,16 @@ def test_expand_host_chunk_pipeline_equals_single_pass(oracle, robot_type, n_chu
         for name in ("row_ptr", "prim_idx", "delta_dist", "status", "chosen_index", "cost_motion",
                      "jump_lbt", "h", "x_final"):
             assert np.array_equal(getattr(one, name), getattr(two, name)), name
+        # the subset of arrays the db-A* loop reads: the others are not downloaded
+        keep = {k: np.array(getattr(view, k)) for k in ("prim_idx", "status", "chosen_index", "jump_lbt", "h", "x_final")}
+        ex.set_host_outputs(_abi.OUT_SEARCH)
+        part = ex.expand_host(case.nodes, case.radius, case.goal, case.goal_radius, 0, n_chunks=n_chunks)
+        assert part.delta_dist is None and part.valid_slot is None and part.cost_motion is None
+        for k, v in keep.items():
+            assert np.array_equal(getattr(part, k), v), k
+        with pytest.raises(_abi.DynoError):
+            ex.set_host_outputs(_abi.OUT_ALL & ~1)
+        ex.set_host_outputs(_abi.OUT_ALL)
         # capacity errors surface from the pipelined path too
         assert one.n_edges >= 2
         ex.set_capacity(one.n_edges // 2)
