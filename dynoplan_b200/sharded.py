@@ -152,7 +152,7 @@ class ShardedExpander:
             self._bar = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
             dist.barrier(group=self.group)
         self.mailbox = True
-        self.launches_per_step = 8  # merge: scan, fill, sort x4, gather, unpack (dispatch is fused)
+        self.launches_per_step = 3  # merge: scan, rank (merge by ranking), unpack (dispatch is fused)
 
     def _barrier(self):
         if self.world > 1:
