@@ -167,3 +167,51 @@ def finalize_library(lib: MotionLibrary, robot: RobotModel, add_noise: bool = Tr
         q /= np.sqrt((q * q).sum(axis=1, keepdims=True))
     if lib.cost[0] > 1e5:
         lib.cost[:] = robot.ref_dt * (lib.T - 1)
+
+
+def save_motion_primitives(path: str, lib: MotionLibrary, num_motions: int = -1, precision: int = 17) -> None:
+    """Write a library in one of the reference's ``Trajectories`` file formats, chosen by the
+    extension like the readers: ``.msgpack`` / ``.json`` (``save_file_msgpack`` /
+    ``save_file_json``, dynobench/include/dynobench/motions.hpp:336-368: the nlohmann object
+    ``{"data": [{"actions": [...], "states": [...]}]}``), ``.yaml`` (``save_file_yaml``,
+    motions.hpp:292-324: a sequence of ``Trajectory::to_yaml_format`` blocks; the fields the
+    reader needs -- cost, feasible, states, actions -- are written) and ``.bin``
+    (``save_file_boost``).  Files written here load back through the reference's own
+    ``load_motion_primitives_new`` -- and through ours, bit-exactly for msgpack / bin / json."""
+    n = lib.N if num_motions < 0 else min(num_motions, lib.N)
+    trajs = [lib.primitive(i) for i in range(n)]
+    ext = os.path.splitext(path)[1]
+    if ext == ".msgpack":
+        import msgpack
+        obj = {"data": [{"actions": u.tolist(), "states": s.tolist()} for s, u in trajs]}
+        with open(path, "wb") as f:
+            f.write(msgpack.packb(obj, use_single_float=False))
+    elif ext == ".json":
+        obj = {"data": [{"actions": u.tolist(), "states": s.tolist()} for s, u in trajs]}
+        with open(path, "w") as f:
+            json.dump(obj, f)
+    elif ext == ".yaml":
+        fmt = "%." + str(precision) + "g"
+
+        def row(v):
+            return "[" + ",".join(fmt % x for x in v) + "]"
+        with open(path, "w") as f:
+            for i, (s, u) in enumerate(trajs):
+                f.write("-\n")
+                f.write("  cost: " + fmt % lib.cost[i] + "\n")
+                f.write("  feasible: 1\n")
+                f.write("  start: " + row(s[0]) + "\n")
+                f.write("  goal: " + row(s[-1]) + "\n")
+                f.write("  num_states: %d\n" % len(s))
+                f.write("  states:\n")
+                for x in s:
+                    f.write("    - " + row(x) + "\n")
+                f.write("  num_actions: %d\n" % len(u))
+                f.write("  actions:\n")
+                for x in u:
+                    f.write("    - " + row(x) + "\n")
+    elif ext == ".bin":
+        from .boost_archive import write_trajectories_boost
+        write_trajectories_boost(path, [(s, u, lib.cost[i]) for i, (s, u) in enumerate(trajs)])
+    else:
+        raise RuntimeError("Incompatible format for motion primitives: " + path)

@@ -115,6 +115,11 @@ def golden_problem(system: str, env: str) -> Problem:
     return Problem.from_yaml(os.path.join(GOLDEN, "envs", system, env + ".yaml"))
 
 
+def first_env(system: str) -> str:
+    """Name of the first committed environment of a system (alphabetical)."""
+    return sorted(f[:-5] for f in os.listdir(os.path.join(GOLDEN, "envs", system)) if f.endswith(".yaml"))[0]
+
+
 @dataclass
 class ParityReport:
     n_edges: int = 0
