@@ -51,15 +51,17 @@ def test_full_size_expansion_properties(oracle, n_prims, n_obs):
     case = testing.synthetic_case("quad3d_v0", n_prims, B, seed=0, delta=.8, alpha=.5, n_obs=n_obs)
     rng = np.random.default_rng(7)
     pick = np.sort(rng.choice(B, size=40, replace=False))
+    fields = ("row_ptr", "prim_idx", "delta_dist", "status", "valid_slot", "chosen_index", "cost_motion",
+              "jump_lbt", "h", "x_final")
     with GpuExpander(case.robot, case.obstacles, case.library, capacity=1 << 24) as ex:
         got = ex.expand(case.nodes, case.radius, case.goal, case.goal_radius, 0)
         again = ex.expand(case.nodes, case.radius, case.goal, case.goal_radius, 0)
+        # expand_host returns views of handle-owned pinned memory (valid until the next call): copy
         piped = ex.expand_host(case.nodes, case.radius, case.goal, case.goal_radius, 0).dense()
+        piped = type(piped)(*[np.array(getattr(piped, f)) for f in fields])
         sub = ex.expand(case.nodes[pick], case.radius, case.goal, case.goal_radius, 0)
     assert got.n_edges > 100 * B  # a real workload
     _check_invariants(got, case, B)
-    fields = ("row_ptr", "prim_idx", "delta_dist", "status", "valid_slot", "chosen_index", "cost_motion",
-              "jump_lbt", "h", "x_final")
     # determinism, and the chunk-pipelined host path delivers the same records
     gd = got.dense()
     for name in fields:
