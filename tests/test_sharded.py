@@ -221,6 +221,8 @@ def test_cuda_mailbox_transport_equals_the_unsharded_expansion(robot_type, G):
         full = ex.expand(nodes, case.radius, case.goal, case.goal_radius, 0).dense()
     sb, sl = sharded.shard_bounds(lib.N, G), sharded.node_slices(B, G)
     exs = [GpuExpander(case.robot, case.obstacles, lib.slice(sb[r], sb[r + 1])) for r in range(G)]
+    for r, e in enumerate(exs):
+        e.library_T = lib.T[sb[r]:sb[r + 1]]
     try:
         L = _abi.lib()
         cap_l, cap_h = full.n_edges + 16, int((full.status == 0).sum()) + 16
@@ -251,6 +253,15 @@ def test_cuda_mailbox_transport_equals_the_unsharded_expansion(robot_type, G):
                              "h", "x_final"):
                     assert np.array_equal(getattr(got, name), getattr(full, name)[e0:e1]), (q, name)
                 n_valid_total += int((got.status == 0).sum())
+                # live download: only the offset-dependent components of x_final cross PCIe; with
+                # every shard's final-state table they give back the full rows bit for bit
+                sx.set_final_tables([(sb[r], e.library_T, np.array(e.final_table())) for r, e in enumerate(exs)])
+                lv = sx.fetch(live=True)
+                assert lv.x_final.shape == (int((got.status == 0).sum()), exs[0].live_layout()[0])
+                xs = sx.assemble_x_final(lv)
+                okm = lv.status == 0
+                assert np.array_equal(xs[lv.valid_slot[okm]], full.x_final[e0:e1][okm])
+                assert np.array_equal(lv.prim_idx, got.prim_idx) and np.array_equal(lv.h[lv.valid_slot[okm]], got.h[okm])
             assert n_valid_total == int((full.status == 0).sum())
         # a mailbox region that is too small is an error, not a truncation
         ipc = C.create_string_buffer(64)
