@@ -1,0 +1,59 @@
+"""bench.py's output contract (the driver parses ONE JSON line from stdout) and the committed
+bench lines under profiles/: every key the contract names is present and consistent."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_stdout_carries_only_the_json_line():
+    code = ("import os, bench; bench.quiet_stdout(); print('library noise'); os.system('echo c-level noise'); "
+            "bench.emit({'metric': 'm', 'value': 1.0})")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, check=True)
+    assert r.stdout.splitlines() == ['{"metric": "m", "value": 1.0}']
+    assert "library noise" in r.stderr and "c-level noise" in r.stderr
+
+
+def _line(name):
+    with open(os.path.join(ROOT, "profiles", name)) as f:
+        return json.loads(f.read())
+
+
+def test_committed_bench_lines_have_every_contract_key():
+    with open(os.path.join(ROOT, "BASELINE.json")) as f:
+        baseline = json.load(f)
+    for name, n in (("r1_bench_n1.json", 1), ("r1_bench_n2.json", 2), ("r1_bench_n4.json", 4), ("r1_bench_n8.json", 8)):
+        d = _line(name)
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                  "scaling", "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline",
+                  "cpu_baseline", "clocks"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["warmup"] >= 3 and d["higher_is_better"] is True
+        assert d["metric"].split(" (")[0] in baseline["metric"] and d["dtype"] == "f64" and d["scaling"] == "weak"
+        assert d["vs_baseline"] is None  # BASELINE.md holds no published number for this metric
+        assert "workload" in d["config"] and "model" not in d["config"]
+        for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+            assert k in d["e2e"], (name, k)
+        assert d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] > 0
+        r = d["roofline"]
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        c = d["cpu_baseline"]
+        assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+        assert d["gpu_launches"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        # value = whole-job units / time
+        cfg = d["config"]
+        checks = cfg["n_nodes"] * cfg["n_primitives_per_gpu"] * n
+        assert abs(d["value"] - checks / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
+
+
+def test_reference_arm_line():
+    d = _line("r1_bench_ref.json")
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] == d["cpu_baseline"]["value"]
+    # the headline ratio the driver computes: e2e of our arm / the reference arm
+    ours = _line("r1_bench_n1.json")
+    assert ours["e2e"]["value"] / d["value"] > 100  # north_star: >= 100x the host-core reference
