@@ -109,3 +109,20 @@ def test_host_loop_termination_modes(host_loop, oracle, golden_dir):
                        max_expands=7)
     assert not got["solved"] and got["expands"] == want.summary["expands"] == 7
     assert np.array_equal(got["motions"], want.motions_used)  # plan to the node closest to the goal
+
+
+def test_host_loop_quadrotor_bounded_search(host_loop, oracle, golden_dir):
+    """quad3d: the T_n query's lower bound (translational + rate blocks before the SO(3) acos)
+    and the 3-D hash grid; a bounded number of expansions, plan to the node closest to the goal."""
+    from dynoplan_b200.problem import BOX, Obstacle
+    robot = robot_factory("quad3d_v0", [-4.0] * 3, [4.0] * 3)
+    obstacles = [Obstacle(BOX, [1.0, .5, .3], [.4, 2.0, 2.0]), Obstacle(BOX, [-1.0, -1.0, 0.0], [.5, .5, 3.0])]
+    start = [0.0] * 3 + [0, 0, 0, 1.0] + [0.0] * 6
+    goal = [2.0, 1.0, .5] + [0, 0, 0, 1.0] + [0.0] * 6
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", "quadrotor_v0.msgpack"), robot, 400, rand_seed=1)
+    got, want = _solve(host_loop, oracle, robot, obstacles, lib, start, goal, delta=1.5, max_motions=400,
+                       max_expands=400, limit_branching_factor=30, search_timelimit=120e3, max_batch=128)
+    s = want.summary
+    assert got["expands"] == s["expands"] == 400 and got["n_nodes"] == s["n_nodes"] > 1000
+    assert np.array_equal(got["motions"], want.motions_used)
+    assert got["states"].shape == want.states.shape and np.allclose(got["states"], want.states, rtol=0, atol=1e-12)
