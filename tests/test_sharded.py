@@ -276,3 +276,36 @@ def test_cuda_mailbox_transport_equals_the_unsharded_expansion(robot_type, G):
     finally:
         for ex in exs:
             ex.close()
+
+
+def test_live_final_states_assembly_over_shards_is_pure_table_lookup():
+    """Host logic of the sharded live fetch (no GPU): a final state = the owning shard's table
+    row for (primitive, check_goal slot) with the live components overwritten."""
+    from dynoplan_b200.expander import Edges
+
+    class FakeExpander:  # what ShardedExpander needs from the handle's Python face
+        nx, _h = 5, None
+
+        def live_layout(self):
+            return 2, [0, 1]
+    rng = np.random.default_rng(3)
+    T0, T1 = np.array([10, 7, 5]), np.array([21, 6])
+    tabs = [rng.normal(size=(3, 5, 5)), rng.normal(size=(2, 5, 5))]
+    sx = sharded.ShardedExpander(FakeExpander(), 0, 2, 0)
+    sx.set_final_tables([(3, T1, tabs[1]), (0, T0, tabs[0])])  # any order; offsets must chain
+    with pytest.raises(RuntimeError):
+        sx.set_final_tables([(0, T0, tabs[0]), (4, T1, tabs[1])])
+    sx.set_final_tables([(0, T0, tabs[0]), (3, T1, tabs[1])])
+    # candidates: global primitives 4, 1, 3, 0; the second one rejected
+    prim = np.array([4, 1, 3, 0], np.int32)
+    status = np.array([0, 2, 0, 0], np.uint8)
+    vslot = np.array([2, -1, 0, 1], np.int32)  # merged results: slots are NOT in CSR order
+    # chosen_index per SLOT: slot 0 -> prim 3 (T=21): idx(nn=1)=int(2/5*21)=8; slot 1 -> prim 0: no hit;
+    # slot 2 -> prim 4 (T=6): idx(nn=0)=int(1/5*6)=1
+    chosen = np.array([8, -1, 1], np.int32)
+    live = rng.normal(size=(3, 2))
+    e = Edges(np.array([0, 4]), prim, np.zeros(4), status, vslot, chosen, np.zeros(3), np.zeros(3), np.zeros(3), live)
+    x = sx.assemble_x_final(e)
+    want = np.stack([tabs[1][0, 1], tabs[0][0, 4], tabs[1][1, 0]])
+    want[:, [0, 1]] = live
+    assert np.array_equal(x, want)
