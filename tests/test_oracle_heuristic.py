@@ -1,0 +1,54 @@
+"""Oracle of the roadmap heuristic (db-A* heuristic = 1; SURVEY 8(f) N2 -- not yet on the
+product path) against the one test the reference holds for it:
+test/dbastar/test_dbastar_0.cpp:64-116 (test_heu_map) -- on unicycle1 bugtrap_0 the values
+h(goal), h(5,5,0), h(4,5.5,1.57), h(1,5,0), h(start) must already be in ascending order."""
+import numpy as np
+import pytest
+
+from dynoplan_b200 import testing
+from dynoplan_b200.robots import robot_factory
+
+
+def test_heu_map_orders_the_reference_probe_states(oracle):
+    p = testing.golden_problem("unicycle1_v0", "bugtrap_0")
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    m = oracle.OracleModel(robot, p.obstacles)
+    # options of the reference test: max_size_heu_map = 2000, num_sample_trials = 4000
+    samples = oracle.HeuristicMap.sample(m, robot, p.start, p.goal, num_sample_trials=4000, max_size_heu_map=2000, seed=0)
+    assert np.array_equal(samples[-1], np.asarray(p.goal, dtype=float)) and len(samples) > 1000
+    hm = oracle.HeuristicMap(m, samples)  # heu_connection_radius 1, heu_resolution .5 (options.hpp:120,141)
+    assert hm.d[-1] == 0 and hm.n_edges > len(samples)
+    probes = [p.goal, [5, 5, 0], [4, 5.5, 1.57], [1, 5, 0], p.start]
+    h = [hm.h(x, p.goal, connect_radius_h=.5) for x in probes]
+    assert h == sorted(h), h
+    assert h[0] < 1e-9 and h[-1] < 1e8  # the goal costs nothing; the start is connected
+    # the roadmap bound dominates the euclidean one behind the bugtrap's walls
+    assert h[-1] > m.lower_bound_time(p.start, p.goal)
+
+
+def test_roadmap_building_blocks(oracle):
+    p = testing.golden_problem("unicycle1_v0", "bugtrap_0")
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    m = oracle.OracleModel(robot, p.obstacles)
+    L = oracle.lib()
+    a, b = np.array([.5, .5, 3.0]), np.array([.5, .5, -3.0])
+    x = np.zeros(3)
+    L.orc_interpolate(m._h, oracle._dp(x), oracle._dp(a), oracle._dp(b), .5)  # so2 interpolation wraps through pi
+    assert abs(abs(x[2]) - np.pi) < .15 and x[0] == .5
+    # an edge through a wall is rejected, a free one accepted
+    free = [o for o in p.obstacles]
+    c = np.array(free[0].center[:2])
+    a, b = np.r_[c + [-1.5, 0], 0.0], np.r_[c + [1.5, 0], 0.0]
+    if L.orc_collision_check(m._h, oracle._dp(a)) and L.orc_collision_check(m._h, oracle._dp(b)):
+        assert not L.orc_check_edge_at_resolution(m._h, oracle._dp(a), oracle._dp(b), .5)
+    assert L.orc_check_edge_at_resolution(m._h, oracle._dp(np.asarray(p.start, float)), oracle._dp(np.asarray(p.start, float)), .5)
+    # acrobot: the reference has no lower_bound_time_pr (NOT_IMPLEMENTED); unicycle2 zeroes v, w
+    p2 = testing.golden_problem("unicycle2_v0", "parallelpark_0")
+    r2 = robot_factory(p2.robotType, p2.p_lb, p2.p_ub)
+    m2 = oracle.OracleModel(r2, p2.obstacles)
+    s2 = oracle.HeuristicMap.sample(m2, r2, p2.start, p2.goal, num_sample_trials=300, max_size_heu_map=200, seed=1)
+    assert np.all(s2[:, 3:] == 0)
+    hm2 = oracle.HeuristicMap(m2, s2)
+    moving = np.array(p2.start, dtype=float)
+    moving[3] = .4
+    assert hm2.h(moving, p2.goal) >= hm2.h(p2.start, p2.goal)  # velocity bound can only raise h
