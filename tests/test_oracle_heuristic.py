@@ -52,3 +52,43 @@ def test_roadmap_building_blocks(oracle):
     moving = np.array(p2.start, dtype=float)
     moving[3] = .4
     assert hm2.h(moving, p2.goal) >= hm2.h(p2.start, p2.goal)  # velocity bound can only raise h
+
+
+def test_product_dijkstra_and_file_format_against_the_oracle_map(oracle, tmp_path):
+    """Host side of N2 in the product (dynoplan_b200/heuristics.py): Dijkstra over the roadmap's
+    edge list and the reference's heu-map file format, against the oracle's map."""
+    from dynoplan_b200 import heuristics
+    p = testing.golden_problem("unicycle1_v0", "bugtrap_0")
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    m = oracle.OracleModel(robot, p.obstacles)
+    samples = oracle.HeuristicMap.sample(m, robot, p.start, p.goal, num_sample_trials=600, max_size_heu_map=250, seed=2)
+    hm = oracle.HeuristicMap(m, samples)
+    L = oracle.lib()
+    edges, weights = [], []
+    for i in range(len(samples)):
+        for j in range(i + 1, len(samples)):
+            if m.distance(samples[i], samples[j]) < 1.0 and \
+                    L.orc_check_edge_at_resolution(m._h, oracle._dp(samples[i]), oracle._dp(samples[j]), .5):
+                edges.append((i, j))
+                weights.append(m.lower_bound_time(samples[i], samples[j]))
+    assert len(edges) == hm.n_edges
+    d, par = heuristics.compute_heuristic_map(len(samples), edges, weights)
+    assert np.allclose(d, hm.d, rtol=1e-12, atol=0) and d[-1] == 0
+    reach = d < heuristics.UNREACHABLE
+    assert np.array_equal(par[~reach], np.arange(len(samples))[~reach])
+    # following the parents reaches the goal with exactly the stored cost
+    w = {e: c for e, c in zip(edges, weights)}
+    for v in np.flatnonzero(reach)[:40]:
+        cost, u = 0.0, int(v)
+        while u != len(samples) - 1:
+            nxt = int(par[u])
+            cost += w[(min(u, nxt), max(u, nxt))]
+            u = nxt
+        assert abs(cost - d[v]) < 1e-9
+    path = str(tmp_path / "heu.yaml")
+    heuristics.write_heu_map(path, samples, d, par, header="# test")
+    xs2, d2, p2 = heuristics.load_heu_map(path)
+    assert np.array_equal(xs2, samples) and np.array_equal(d2, d) and np.array_equal(p2, par)
+    with pytest.raises(RuntimeError):
+        (tmp_path / "bad.yaml").write_text("other: 1\n")
+        heuristics.load_heu_map(str(tmp_path / "bad.yaml"))
