@@ -48,3 +48,32 @@ def test_roadmap_h_matches_oracle(oracle, golden_dir, system, env):
         ex.set_heuristic_map(np.zeros((0, robot.nx)), np.zeros(0))
         with pytest.raises(_abi.DynoError):
             ex.expand(nodes, .2, p.goal, .3, heuristic=1)
+
+
+def test_roadmap_build_matches_oracle(oracle, golden_dir):
+    """Map build on the GPU path: sample filter, O(n^2) edge test, Dijkstra -- against the oracle's
+    map over the SAME samples; then a whole db-A* solve with heuristic = 1."""
+    import os
+    from dynoplan_b200 import heuristics
+    from dynoplan_b200.dbastar import Options_dbastar, dbastar
+    from dynoplan_b200.motions import load_motion_primitives_new
+    p = testing.golden_problem("unicycle1_v0", "bugtrap_0")
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", "unicycle1_v0.msgpack"), robot, 100, rand_seed=1)
+    m = oracle.OracleModel(robot, p.obstacles)
+    with GpuExpander(robot, p.obstacles, lib) as ex:
+        rng = np.random.default_rng(5)
+        probes = np.array([heuristics.sample_uniform(robot, rng) for _ in range(2000)])
+        assert np.array_equal(ex.collision_check(probes), np.array([m.collision_check(x) for x in probes]))
+        xs, d, par = heuristics.generate_heuristic_map(ex, robot, p.start, p.goal, num_sample_trials=1200,
+                                                       max_size_heu_map=500, seed=0)
+        hm = oracle.HeuristicMap(m, xs)
+        assert np.allclose(d, hm.d, rtol=1e-12, atol=0) and d[-1] == 0
+        ex.set_heuristic_map(xs, np.minimum(d, 1e300), connect_radius_h=.5)
+        got = dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, delta=.3, max_motions=100, heuristic=1,
+                                                                search_timelimit=120e3))
+        base = dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, delta=.3, max_motions=100, heuristic=0,
+                                                                 search_timelimit=120e3))
+    assert got.solved and base.solved
+    # the roadmap heuristic is the better informed one behind the bugtrap's walls
+    assert int(got.data["expands"]) < int(base.data["expands"])
