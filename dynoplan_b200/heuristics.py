@@ -83,9 +83,13 @@ def sample_uniform(robot, rng) -> np.ndarray:
     caller's choice of seed, not the reference's."""
     lb, ub = np.asarray(robot.x_lb, dtype=np.float64), np.asarray(robot.x_ub, dtype=np.float64)
     v = lb + (ub - lb) * (.5 * (rng.uniform(-1, 1, size=robot.nx) + 1))
-    for k in {0: (2,), 1: (2,), 2: (2, 3), 3: (2,), 4: (0, 1)}.get(robot.kind, ()):
+    for k in {0: (2,), 1: (2,), 2: (2,), 3: (2,), 4: (0, 1)}.get(robot.kind, ()):
         v[k] = np.pi * rng.uniform(-1, 1)
-    if robot.kind == 5:  # quad3d: a unit quaternion
+    if robot.kind == 2:  # car.cpp:153-159: trailer within diff_max_abs (car.hpp:20: pi / 4) of the car
+        a = v[2] + (np.pi / 4) * rng.uniform(-1, 1)
+        a = np.fmod(a + np.pi, 2 * np.pi)
+        v[3] = (a + 2 * np.pi if a < 0 else a) - np.pi
+    if robot.kind == 5:  # quadrotor.cpp:186-192: a uniformly random unit quaternion
         q = rng.normal(size=4)
         v[3:7] = q / np.linalg.norm(q)
     return v

@@ -366,8 +366,14 @@ class HeuristicMap:
             v = lb + (ub - lb) * (.5 * (rng.uniform(-1, 1, size=nx) + 1))
             if robot.kind in (0, 1, 2, 3):
                 v[2] = np.pi * rng.uniform(-1, 1)
-            if robot.kind == 2:
-                v[3] = np.pi * rng.uniform(-1, 1)
+            if robot.kind == 2:  # car.cpp:153-159, diff_max_abs = pi / 4 (car.hpp:20)
+                a = np.fmod(v[2] + (np.pi / 4) * rng.uniform(-1, 1) + np.pi, 2 * np.pi)
+                v[3] = (a + 2 * np.pi if a < 0 else a) - np.pi
+            if robot.kind == 4:  # acrobot.cpp:87-93
+                v[0], v[1] = np.pi * rng.uniform(-1, 1), np.pi * rng.uniform(-1, 1)
+            if robot.kind == 5:  # quadrotor.cpp:186-192
+                q = rng.normal(size=4)
+                v[3:7] = q / np.linalg.norm(q)
             v = zv(v)
             if lib().orc_collision_check(model._h, _dp(v)):
                 out.append(v)

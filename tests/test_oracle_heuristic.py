@@ -92,3 +92,26 @@ def test_product_dijkstra_and_file_format_against_the_oracle_map(oracle, tmp_pat
     with pytest.raises(RuntimeError):
         (tmp_path / "bad.yaml").write_text("other: 1\n")
         heuristics.load_heu_map(str(tmp_path / "bad.yaml"))
+
+
+@pytest.mark.parametrize("system,env", [("car1_v0", "parallelpark_0"), ("quad2d_v0", "quad_obs_column"),
+                                        ("quadrotor_v0", "recovery_with_obs")])
+def test_roadmap_oracle_on_the_other_models(oracle, system, env):
+    """Sanity of the oracle's roadmap for the models the reference test does not cover: the goal
+    costs nothing, h never drops below the velocity bound, connected probes cost at least the
+    straight-line bound."""
+    p = testing.golden_problem(system, env)
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    m = oracle.OracleModel(robot, p.obstacles)
+    samples = oracle.HeuristicMap.sample(m, robot, p.start, p.goal, num_sample_trials=500, max_size_heu_map=300, seed=3)
+    if robot.kind == 5:
+        assert np.allclose(np.linalg.norm(samples[1:-1, 3:7], axis=1), 1)
+    hm = oracle.HeuristicMap(m, samples, heu_connection_radius=2.0, heu_resolution=.5)
+    R = 1.5
+    goal0 = samples[-1]
+    assert hm.h(goal0, p.goal, R) <= hm.h(p.start, p.goal, R)
+    assert hm.h(goal0, goal0, R) < 1e-9
+    for x in samples[1:40]:
+        hx = hm.h(x, p.goal, R)
+        if hx < 1e8:
+            assert hx >= m.lower_bound_time(np.r_[x], np.r_[goal0]) - 1e-9  # triangle inequality over the roadmap
