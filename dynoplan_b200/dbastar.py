@@ -61,6 +61,16 @@ class Out_info_db:
     actions: Optional[np.ndarray] = None
     motions_used: Optional[np.ndarray] = None
     intermediate_state: Optional[np.ndarray] = None
+    traj: Optional["Trajectory"] = None  # traj_out (dbastar.cpp:1014-1034), ready for to_yaml_format
+
+    def write_yaml(self, out) -> None:
+        """``Out_info_db::write_yaml`` (dbastar.hpp:134-144); ``out`` is a text stream."""
+        from .trajectory import _num
+        out.write(f"cost: {_num(self.cost)}\nsolved: {int(self.solved)}\n")
+        out.write(f"cost_with_delta_time: {_num(self.cost_with_delta_time)}\ntime_search: {_num(self.time_search)}\n")
+        out.write("data:\n")
+        for k in sorted(self.data):  # std::map iterates in key order
+            out.write(f"  {k}: {self.data[k]}\n")
 
 
 def dbastar(expander: GpuExpander, library: MotionLibrary, start, goal,
@@ -110,6 +120,15 @@ def dbastar(expander: GpuExpander, library: MotionLibrary, start, goal,
                     "max_collision": str(res.max_collision), "x_bound_distance": str(res.x_bound_distance),
                     "u_bound_distance": str(res.u_bound_distance), "feasible": str(int(res.feasible))}
         out.feasible = bool(res.feasible)
+        # traj_out: start / goal, Trajectory::check figures, cost, and -- as the last thing dbastar()
+        # does with it -- update_feasibility with the DEFAULT thresholds (dbastar.cpp:1016-1034)
+        from .trajectory import Trajectory
+        out.traj = Trajectory(states=out.states, actions=out.actions, start=start.copy(), goal=goal.copy(),
+                              cost=out.cost, max_jump=float(res.max_jump), max_collision=float(res.max_collision),
+                              goal_distance=float(res.goal_distance), start_distance=float(res.start_distance),
+                              x_bound_distance=float(res.x_bound_distance),
+                              u_bound_distance=float(res.u_bound_distance))
+        out.traj.update_feasibility()
         if out.solved and not out.feasible:  # CHECK(traj_out.feasible, "") (dbastar.cpp:1030)
             raise RuntimeError("db-A* reported SOLVED but the plan fails Trajectory::check: " + str(out.data))
         return out

@@ -110,7 +110,19 @@ def main():
                                     "start_distance", "num_states", "states", "actions")}
         with open(os.path.join(HERE, "ref_solutions", f"{system}__{env}.yaml"), "w") as f:
             yaml.dump(keep, f, Dumper=yaml.CSafeDumper, default_flow_style=None, width=200)
+    # a few stored trajectory files verbatim: the byte-level pin of Trajectory::to_yaml_format
+    os.makedirs(os.path.join(HERE, "trajectories"), exist_ok=True)
+    for rel in RAW_TRAJECTORIES:
+        shutil.copy(REF + "dynobench/envs/" + rel, os.path.join(HERE, "trajectories", rel.replace("/", "__")))
     make_expand_fixtures()
+
+
+RAW_TRAJECTORIES = ["unicycle1_v0/parallelpark_0/idbastar_v0_db_solution_v0.yaml",
+                    "unicycle1_v0/parallelpark_0/idbastar_v0_solution_v0.yaml",   # times + info
+                    "unicycle1_v0/parallelpark_0/rrt_to_v0_guess_v0.yaml",
+                    "quadrotor_v0/empty_0_easy/idbastar_v0_db_solution_v0.yaml",  # a single state, no actions
+                    "quad2d_v0/empty_0/rrt_to_v0_guess_v0.yaml",
+                    "car1_v0/kink_0/idbastar_v0_db_solution_v0.yaml"]
 
 
 def make_expand_fixtures():
