@@ -21,8 +21,44 @@ from .motions import MotionLibrary
 TERMINATE_STATUS = ["SOLVED", "MAX_EXPANDS", "EMPTY_QUEUE", "MAX_TIME", "UNKNOWN"]  # dbastar.hpp:109-127
 
 
+def _ostream(v) -> str:
+    """A value through ``std::ostream`` (bools as 0 / 1, doubles with 6 significant digits)."""
+    if isinstance(v, bool):
+        return str(int(v))
+    if isinstance(v, float):
+        from .trajectory import _num
+        return _num(v)
+    return str(v)
+
+
+class _YamlOptions:
+    """``read_from_yaml`` / ``print`` of the reference's option structs: a file (or node) either holds
+    the keys at the top level or under ``yaml_key``; only the keys in ``yaml_fields`` are read, in
+    that order, and a key that is absent keeps its value (set_from_yaml, general_utils.hpp:300-340)."""
+    yaml_key = ""
+    yaml_fields: tuple = ()
+
+    def read_from_yaml(self, src):
+        if isinstance(src, str):
+            import yaml
+            with open(src) as f:
+                src = yaml.safe_load(f) or {}
+        node = src.get(self.yaml_key, src) if isinstance(src, dict) else {}
+        for k in self.yaml_fields:
+            if k in node and hasattr(self, k):
+                cur = getattr(self, k)
+                v = node[k]
+                setattr(self, k, bool(v) if isinstance(cur, bool) else type(cur)(v))
+        return self
+
+    def print(self, out, be: str = "", af: str = ": ") -> None:
+        for k in self.yaml_fields:
+            if hasattr(self, k):
+                out.write(f"{be}{k}{af}{_ostream(getattr(self, k))}\n")
+
+
 @dataclass
-class Options_dbastar:
+class Options_dbastar(_YamlOptions):
     fix_seed: bool = False
     delta: float = .3
     alpha: float = .5
@@ -34,6 +70,14 @@ class Options_dbastar:
     limit_branching_factor: int = 20
     search_timelimit: float = 1e4  # ms
     max_batch: int = 256  # ours: open nodes expanded per GPU call
+    # Options_dbastar::__load_data (src/dbastar/options.cpp:16-42): keys and their order
+    yaml_key = "options_dbastar"
+    yaml_fields = ("fix_seed", "new_invariance", "connect_radius_h", "use_collision_shape", "delta", "alpha",
+                   "maxCost", "heuristic", "max_motions", "heu_resolution", "delta_factor_goal",
+                   "cost_delta_factor", "num_sample_trials", "max_expands", "cut_actions",
+                   "limit_branching_factor", "debug", "add_after_expand", "motionsFile", "outFile",
+                   "search_timelimit", "max_size_heu_map", "heu_map_file", "heu_connection_radius",
+                   "use_nigh_nn", "check_cols")
     # parsed by the reference, never read by dbastar.cpp
     connect_radius_h: float = .5
     motionsFile: str = ""
@@ -46,6 +90,11 @@ class Options_dbastar:
     add_after_expand: bool = False
     check_cols: bool = True
     use_nigh_nn: bool = True
+    heu_connection_radius: float = 1.0
+    heu_map_file: str = ""
+    max_size_heu_map: int = 1000
+    num_sample_trials: int = 3000
+    heu_resolution: float = .5
 
 
 @dataclass

@@ -25,14 +25,17 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
-from .dbastar import Options_dbastar, Out_info_db, dbastar
+from .dbastar import _YamlOptions, Options_dbastar, Out_info_db, dbastar
 from .expander import GpuExpander
 from .motions import MotionLibrary, _LibcRand
 from .robots import ACROBOT, QUAD2D, QUAD3D, RobotModel
 
 
 @dataclass
-class Options_idbAStar:  # idbastar.hpp:46-58
+class Options_idbAStar(_YamlOptions):  # idbastar.hpp:46-58 (+ read_from_yaml / print, :61-109)
+    yaml_key = "options_idbastar"
+    yaml_fields = ("delta_0", "num_primitives_0", "delta_rate", "num_primitives_rate", "timelimit", "max_it",
+                   "new_schedule", "max_motions_primitives", "add_primitives_opt")
     delta_0: float = .3
     num_primitives_0: int = 1000
     delta_rate: float = .9

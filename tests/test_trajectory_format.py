@@ -60,3 +60,30 @@ def test_result_layouts_and_formatting():
     text = t.to_yaml_format()
     assert "  - [1e-05,-0,1.23457e+08,0.333333]\n" in text
     assert "start: [0,0]\ngoal: [1,1]\n" in text and "cost: 1e+08\n" in text and "num_actions: 0\nactions:\n" in text
+
+
+def test_options_read_from_yaml_and_print(tmp_path):
+    """Options_dbastar / Options_idbAStar: read_from_yaml with the keys at the top level or under
+    options_dbastar / options_idbastar (options.cpp:55-73, idbastar.hpp:87-109), unknown keys
+    ignored, absent keys keep their value; print() in the reference's key order and formatting."""
+    from dynoplan_b200.dbastar import Options_dbastar
+    from dynoplan_b200.idbastar import Options_idbAStar
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text("options_dbastar:\n  delta: .25\n  max_motions: 400\n  fix_seed: 1\n  heuristic: 1\n  solver_id: 1\n"
+                   "options_idbastar:\n  delta_0: .5\n  num_primitives_0: 200\n  new_schedule: false\n")
+    o = Options_dbastar().read_from_yaml(str(cfg))
+    assert (o.delta, o.max_motions, o.fix_seed, o.heuristic, o.alpha) == (.25, 400, True, 1, .5)
+    assert isinstance(o.max_motions, int) and isinstance(o.fix_seed, bool)
+    i = Options_idbAStar().read_from_yaml(str(cfg))
+    assert (i.delta_0, i.num_primitives_0, i.new_schedule, i.max_it) == (.5, 200, False, 10)
+    flat = Options_dbastar().read_from_yaml({"delta": .7, "search_timelimit": 15000, "smooth_traj": True})
+    assert flat.delta == .7 and flat.search_timelimit == 15000.0
+    s = io.StringIO()
+    i.print(s, "  ")
+    assert s.getvalue() == ("  delta_0: 0.5\n  num_primitives_0: 200\n  delta_rate: 0.9\n  num_primitives_rate: 1.5\n"
+                            "  timelimit: 10\n  max_it: 10\n  new_schedule: 0\n  max_motions_primitives: 10000\n"
+                            "  add_primitives_opt: 1\n")
+    s = io.StringIO()
+    o.print(s)
+    lines = s.getvalue().splitlines()
+    assert lines[0] == "fix_seed: 1" and lines[4] == "delta: 0.25" and lines[-1] == "check_cols: 1" and len(lines) == 26
