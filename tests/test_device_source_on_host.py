@@ -256,3 +256,38 @@ def test_device_roadmap_edges_and_heuristic(dev, oracle, golden_dir, system):
             assert got == want.h(x, goal, cr)
             finite += got < 1e7
     assert err.value == 0 and finite > 5
+
+
+@pytest.mark.parametrize("system", SYSTEMS)
+def test_device_nigh_metric_on_the_boundary(dev, oracle, golden_dir, system):
+    """The delta decision at its edge (one flipped decision desynchronises the search):
+    radius exactly the distance (accepted, `<=`), one ulp below (rejected), angles across the
+    +-pi seam, antipodal quaternions (the same rotation), identical states."""
+    p, robot, lib = _setup(golden_dir, system)
+    m = oracle.OracleModel(robot, p.obstacles)
+    d = Dev(dev, robot, p.obstacles)
+    rng = np.random.default_rng(8)
+    xs, ys = _states(robot, lib, p, rng, 200), _states(robot, lib, p, rng, 200)
+    ys[:120] = xs[:120] + rng.normal(0, .02, size=(120, robot.nx))
+    ang = {0: [2], 1: [2], 2: [2, 3], 3: [2], 4: [0, 1], 5: []}[robot.kind]
+    for k in ang:  # pairs straddling the seam
+        xs[40:80, k] = np.pi - rng.uniform(0, 1e-3, 40)
+        ys[40:80, k] = -np.pi + rng.uniform(0, 1e-3, 40)
+    if robot.kind == 5:
+        ys[:, 3:7] /= np.linalg.norm(ys[:, 3:7], axis=1, keepdims=True)
+        ys[80:120, 3:7] = -xs[80:120, 3:7]  # q and -q
+    ys[120:140] = xs[120:140]  # identical
+    dist = C.c_double(0)
+    for x, y in zip(xs, ys):
+        x, y = np.ascontiguousarray(x), np.ascontiguousarray(y)
+        want = m.nigh_distance(x, y)
+        assert dev.dh_nigh_within(d.h, P(x), P(y), want, C.byref(dist)) == 1 and dist.value == want
+        if want > 0:
+            assert dev.dh_nigh_within(d.h, P(x), P(y), np.nextafter(want, 0.0), C.byref(dist)) == 0
+        assert dev.dh_nigh_within(d.h, P(x), P(y), np.nextafter(want, np.inf), C.byref(dist)) == 1 and dist.value == want
+    seam = [m.nigh_distance(x, y) for x, y in zip(xs[40:80], ys[40:80])]
+    if ang:
+        assert max(seam) < 1.0  # the seam pairs are close (only their positions differ), not 2*pi apart
+    if robot.kind == 5:
+        flipped = [m.nigh_distance(x, y) for x, y in zip(xs[80:120], ys[80:120])]
+        assert max(flipped) < 1e-6 + max(np.linalg.norm(xs[80:120, :3] - ys[80:120, :3], axis=1).max() * 2, 1)
