@@ -113,7 +113,8 @@ EdgeResult check_edge(const Model &m, const Library &lib, int64_t prim,
   }
 
   // heuristic (heuristics.hpp:115-130 Heu_euclidean, Heu_blind)
-  r.h = heuristic == 0 ? m.lower_bound_time(r.x_final, goal, err) : 0.0;
+  r.h = heuristic == 0 ? m.lower_bound_time(r.x_final, goal, err)
+                       : (heuristic == 1 ? m.roadmap_h(r.x_final, goal) : 0.0); // Heu_roadmap (heuristics.hpp:161-185)
 
   // dbastar.cpp:837-847
   r.cost_motion = r.chosen_index != -1 ? r.chosen_index * m.d.ref_dt
@@ -327,7 +328,7 @@ SearchResult dbastar(const Model &m, const Library &lib, const double *start,
   T_n.init(&m, &nodes, novelty_radius);
 
   auto h_fun = [&](const double *x) {
-    return opt.heuristic == 0 ? m.lower_bound_time(x, goal, &res.err) : 0.0;
+    return opt.heuristic == 0 ? m.lower_bound_time(x, goal, &res.err) : (opt.heuristic == 1 ? m.roadmap_h(x, goal) : 0.0);
   };
 
   { // start node (:642-651)

@@ -268,9 +268,22 @@ static double roadmap_h(const Model &m, const HeuMap &map, const double *x, cons
   return std::max(lower_bound_time_vel(m, x, goal), pos_h);
 }
 
+double Model::roadmap_h(const double *x, const double *goal) const {
+  if (!heu_map)
+    throw std::runtime_error("heuristic = 1 without a roadmap (orc_model_set_heu_map)");
+  return orc::roadmap_h(*this, *heu_map, x, goal, connect_radius_h);
+}
+
 } // namespace orc
 
 extern "C" {
+double orc_model_roadmap_h(void *m, const double *x, const double *goal) {
+  return ((orc::Model *)m)->roadmap_h(x, goal);
+}
+void orc_model_set_heu_map(void *m, void *map, double connect_radius_h) {
+  ((orc::Model *)m)->heu_map = (const orc::HeuMap *)map;
+  ((orc::Model *)m)->connect_radius_h = connect_radius_h;
+}
 void *orc_heu_build(void *m, const double *samples, int n, double distance_threshold, double resolution) {
   return orc::build_map(*(orc::Model *)m, samples, n, distance_threshold, resolution);
 }

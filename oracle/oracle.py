@@ -122,6 +122,9 @@ def lib():
         L.orc_heu_copy.argtypes = [vp, dp, C.POINTER(C.c_int)]
         L.orc_heu_h.restype = C.c_double
         L.orc_heu_h.argtypes = [vp, vp, dp, dp, C.c_double]
+        L.orc_model_set_heu_map.argtypes = [vp, vp, C.c_double]
+        L.orc_model_roadmap_h.restype = C.c_double
+        L.orc_model_roadmap_h.argtypes = [vp, dp, dp]
         L.orc_check_edge_at_resolution.argtypes = [vp, dp, dp, C.c_double]
         L.orc_interpolate.argtypes = [vp, dp, dp, dp, C.c_double]
         _lib = L
@@ -332,6 +335,11 @@ class HeuristicMap:
         self.parent = np.zeros(n, dtype=np.int32)
         lib().orc_heu_copy(self._h, _dp(self.d), self.parent.ctypes.data_as(C.POINTER(C.c_int)))
         self.n_edges = int(lib().orc_heu_edges(self._h))
+
+    def attach(self, connect_radius_h: float = .5) -> None:
+        """Make this the model's roadmap: ``expand`` / ``dbastar`` with ``heuristic = 1`` query it."""
+        self.model._heu_keep = self  # the model does not own the map
+        lib().orc_model_set_heu_map(self.model._h, self._h, float(connect_radius_h))
 
     def h(self, x, goal, connect_radius_h: float = .5) -> float:
         return float(lib().orc_heu_h(self.model._h, self._h, _dp(_vec(x)), _dp(_vec(goal)), float(connect_radius_h)))
