@@ -62,6 +62,66 @@ class Info_out_idbastar:  # dynobench::Info_out + exit_criteria (idbastar.hpp:38
     actions: Optional[np.ndarray] = None
     library_size: int = 0
     library: Optional[MotionLibrary] = None  # the library after the last iteration (grown at the front)
+    infos_opt: List[dict] = field(default_factory=list)
+
+    def _trajs(self, which: str):
+        """``Trajectory`` objects of ``trajs_raw`` (every db-A* plan) or ``trajs_opt`` (what the
+        optimiser returned: start / goal, cost and feasibility from its verdict)."""
+        from .trajectory import Trajectory
+        if which == "raw":
+            return [o.traj for o in self.trajs_raw if o.traj is not None]
+        ref = self.trajs_raw[0].traj if self.trajs_raw and self.trajs_raw[0].traj is not None else None
+        out = []
+        for xs, us, feasible, cost in self.trajs_opt:
+            t = Trajectory(states=np.asarray(xs), actions=np.asarray(us), cost=float(cost), feasible=bool(feasible))
+            if ref is not None:
+                t.start, t.goal = ref.start, ref.goal
+            out.append(t)
+        return out
+
+    def to_yaml(self, out, be: str = "", af: str = ": ") -> None:
+        """``Info_out::to_yaml`` (dynobench/src/motions.cpp:553-591): the body of the results file
+        the reference's benchmark scripts parse."""
+        from .dbastar import _ostream
+        prefix = "   "
+        out.write(f"{be}solved{af}{int(self.solved)}\n{be}solved_raw{af}{int(self.solved_raw)}\n")
+        out.write(f"{be}cost{af}{_ostream(float(self.cost))}\n")
+        opt, raw = self._trajs("opt"), self._trajs("raw")
+        out.write(f"{be}trajs_opt_size: {len(opt)}\n{be}trajs_opt{af}\n")
+        for t in opt:
+            out.write(f"{be}  -\n")
+            t.to_yaml_format(out, be + prefix)
+        out.write(f"{be}trajs_raw_size: {len(raw)}\ntrajs_raw:\n")
+        for t in raw:
+            out.write(f"{be}  -\n")
+            t.to_yaml_format(out, be + prefix)
+        for name, infos in (("infos_opt", self.infos_opt), ("infos_raw", self.infos_raw)):
+            out.write(f"{name}:\n")
+            for d in infos:
+                out.write(f"{be}  -\n")
+                for k in sorted(d):  # std::map order
+                    out.write(f"{be}{prefix}{k}: {d[k]}\n")
+
+    def print_trajs(self, path: str) -> None:
+        """``Info_out::print_trajs`` (motions.cpp:537-551): ``<path>.trajopt-<i>.yaml`` / ``.trajraw-<i>.yaml``."""
+        for name, which in (("trajopt", "opt"), ("trajraw", "raw")):
+            for i, t in enumerate(self._trajs(which)):
+                t.to_yaml_format(f"{path}.{name}-{i}.yaml")
+
+
+def write_results_idbastar(results_file: str, problem, options_idbastar: Options_idbAStar,
+                           options_dbastar: Options_dbastar, info: Info_out_idbastar, time_stamp: str = "") -> None:
+    """``write_results_idbastar`` (src/idbastar/idbastar.cpp:336-360).  The trajectory optimiser is a
+    callable here, so ``options trajopt:`` stays empty."""
+    with open(results_file, "w") as f:
+        f.write(f"alg: idbastar\nproblem_file: {getattr(problem, 'file', '')}\nrobot_type: {problem.robotType}\n")
+        f.write(f"time_stamp: {time_stamp}\n")
+        f.write("options_idbastar:\n")
+        options_idbastar.print(f, "  ")
+        f.write("options_dbastar:\n")
+        options_dbastar.print(f, "  ")
+        f.write("options trajopt:\n")
+        info.to_yaml(f)
 
 
 def schedule(options: Options_idbAStar, solved_history: List[bool]):

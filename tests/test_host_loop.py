@@ -244,6 +244,29 @@ def test_idbastar_outer_loop_on_the_cpu(host_loop, oracle, golden_dir, monkeypat
     assert info.trajs_raw[1].solved and info.trajs_raw[1].motions_used.min() < 5
     assert info.cost <= robot.ref_dt * calls[0] + 1e-12
     host_loop.mock_destroy(ex._h)
+    # the results file (write_results_idbastar + Info_out::to_yaml) parses as yaml and carries
+    # every iteration's plan in the Trajectory format; print_trajs writes one file per plan
+    import io
+    import yaml
+    from dynoplan_b200.idbastar import write_results_idbastar
+    from dynoplan_b200.trajectory import Trajectory
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "results.yaml")
+        write_results_idbastar(path, p, oi, Options_dbastar(fix_seed=True), info, time_stamp="now")
+        with open(path) as f:
+            text = f.read()
+        doc = yaml.safe_load(text)
+        assert doc["alg"] == "idbastar" and doc["robot_type"] == p.robotType and doc["solved"] == 1
+        assert doc["options_idbastar"]["num_primitives_0"] == 100 and doc["options_dbastar"]["fix_seed"] == 1
+        assert doc["trajs_raw_size"] == 3 == len(doc["trajs_raw"]) and doc["trajs_opt_size"] == len(doc["trajs_opt"]) == len(calls)
+        assert doc["trajs_raw"][0]["num_states"] == info.trajs_raw[0].states.shape[0]
+        assert np.allclose(doc["trajs_raw"][0]["states"], info.trajs_raw[0].states, rtol=1.1e-5, atol=2e-6)
+        assert doc["infos_raw"][0]["terminate_status"] == "SOLVED"
+        info.print_trajs(path)
+        back = Trajectory.read_from_yaml(path + ".trajraw-1.yaml")
+        assert back.states.shape == info.trajs_raw[1].states.shape
+        assert os.path.exists(path + f".trajopt-{len(calls) - 1}.yaml")
 
 
 @pytest.mark.parametrize("system,env,n_prims,delta", [("unicycle1_v0", "parallelpark_0", 100, .3), ("car1_v0", "kink_0", 400, .3)])
