@@ -5,6 +5,7 @@
 // the _rn intrinsics below must stay separate IEEE operations, as they are on the device.
 #pragma once
 #define _GNU_SOURCE 1
+#include <algorithm>
 #include <cmath>
 #include <math.h>
 #define __device__
@@ -12,7 +13,8 @@
 #define __global__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static // kernel_emu.hpp: blocks run one after the other
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
