@@ -1,0 +1,61 @@
+"""TEST INFRASTRUCTURE ONLY: builds ``libdynoplan_emu.so`` -- the product's CUDA source
+(dynoplan_b200/csrc/*.cu, *.cuh: every kernel and the ABI's host code) compiled by g++ for the
+CPU, so that the CPU suite can run the real kernels on tiny cases against the oracle
+(tests/test_cuda_source_on_cpu.py).
+
+How: the sources are COPIED to tests/cuda_emu/_build/gen with four textual rewrites -- the
+``<<<grid, block, smem, stream>>>`` launch syntax becomes ``emu_cfg(kernel, grid, block, smem,
+stream)(args)``, ``extern __shared__ T name[]`` becomes a pointer to the launch's dynamic shared
+memory buffer, the two inline-PTX statements (an L2 prefetch, the approximate square root) become a
+no-op and ``std::sqrt`` -- and compiled against
+tests/device_host/shim (CUDA qualifiers and intrinsics as plain C++, a block = OS threads with
+barriers, the runtime API served by the host).  Nothing here is shipped or importable from the
+package: the product library has no CPU path and refuses to start without a CUDA device."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "dynoplan_b200", "csrc")
+SHIM = os.path.join(os.path.dirname(HERE), "device_host", "shim")
+GEN = os.path.join(HERE, "_build", "gen")
+OUT = os.path.join(HERE, "_build", "libdynoplan_emu.so")
+
+LAUNCH = re.compile(r"(\bk_\w+(?:<[^;(){}<>]*>)?)\s*<<<(.*?)>>>\s*\(", re.S)
+DYN_SMEM = re.compile(r"extern __shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];")
+ASM = re.compile(r'asm volatile\("prefetch[^"]*"[^;]*;')
+SQRT_APPROX = re.compile(r'asm\("sqrt\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((\w+)\)\);')
+
+
+def rewrite(text: str) -> str:
+    text = SQRT_APPROX.sub(r"\1 = std::sqrt(\2);", text)  # the MUFU square root (2 ulp) -> the exact one
+    text = ASM.sub("((void)0);", text)
+    text = DYN_SMEM.sub(r"\1 *\2 = reinterpret_cast<\1 *>(emu_dyn_smem_ptr());", text)
+    text = LAUNCH.sub(r"emu_cfg(\1, \2)(", text)
+    return text.replace('"../../include/dynoplan_b200.h"', '"dynoplan_b200.h"')
+
+
+def build(force: bool = False) -> str:
+    os.makedirs(GEN, exist_ok=True)
+    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".hpp")))
+    deps = [os.path.join(CSRC, f) for f in srcs] + [os.path.join(SHIM, f) for f in os.listdir(SHIM)] + [__file__]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    units = []
+    for f in srcs:
+        with open(os.path.join(CSRC, f)) as fh:
+            text = rewrite(fh.read())
+        assert "<<<" not in text and "extern __shared__" not in text, f
+        name = f[:-3] + ".cpp" if f.endswith(".cu") else f
+        with open(os.path.join(GEN, name), "w") as fh:
+            fh.write(text)
+        if name.endswith(".cpp"):
+            units.append(os.path.join(GEN, name))
+    subprocess.run(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w",
+                    "-I", SHIM, "-I", os.path.join(ROOT, "include"), "-I", GEN, "-o", OUT] + units, check=True)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))

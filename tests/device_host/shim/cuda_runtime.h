@@ -20,4 +20,5 @@ inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+#include "cuda_api_emu.hpp" // the runtime calls, vector types, conversions (tests/cuda_emu)
 #include "kernel_emu.hpp" // threadIdx / blockIdx, warp shuffles, emu_launch: the kernels themselves

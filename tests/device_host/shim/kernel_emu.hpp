@@ -9,9 +9,11 @@
 // every barrier it would reach on the device.
 #pragma once
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 struct EmuDim {
@@ -82,15 +84,20 @@ inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int atomicOr(int *p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
-inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
-  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+template <class T, class V> inline T atomicAdd(T *p, V v) { return __atomic_fetch_add(p, (T)v, __ATOMIC_RELAXED); }
+
+// dynamic shared memory of the running block (`extern __shared__ T name[]` is rewritten to a
+// pointer to it in the generated copies of the kernel sources, tests/cuda_emu)
+inline unsigned char *&emu_dyn_smem_ptr() {
+  static unsigned char *p = nullptr;
+  return p;
 }
 
 // kernel<<<grid, block>>>(args...)  ->  emu_launch(grid, block, [&] { kernel(args...); })
-template <typename F> void emu_launch(unsigned grid, unsigned block, F body) {
-  gridDim.x = grid, blockDim.x = block;
+template <typename F> void emu_launch(unsigned grid, unsigned block, F body, unsigned grid_y = 1) {
+  gridDim.x = grid, gridDim.y = grid_y, blockDim.x = block;
   const unsigned n_warps = (block + 31) / 32;
+  for (unsigned by = 0; by < grid_y; by++)
   for (unsigned b = 0; b < grid; b++) {
     EmuBarrier block_bar;
     block_bar.parties = (int)block;
@@ -100,11 +107,35 @@ template <typename F> void emu_launch(unsigned grid, unsigned block, F body) {
     std::vector<std::thread> threads;
     for (unsigned t = 0; t < block; t++)
       threads.emplace_back([&, t] {
-        threadIdx.x = t, blockIdx.x = b;
+        threadIdx.x = t, blockIdx.x = b, blockIdx.y = by;
         emu_warp = &warps[t / 32], emu_block = &block_bar, emu_lane = (int)(t & 31);
         body();
       });
     for (auto &th : threads)
       th.join();
   }
+}
+
+// kernel<<<grid, block, smem, stream>>>(args...) is rewritten to emu_cfg(kernel, grid, block, smem, stream)(args...)
+// in the generated copies of the sources: runs the launch synchronously.
+template <typename K> struct EmuLaunch {
+  K kernel;
+  unsigned gx, gy, block;
+  size_t smem;
+  template <typename... A> void operator()(const A &...args) const {
+    unsigned char *buf = smem ? (unsigned char *)std::aligned_alloc(128, (smem + 127) / 128 * 128) : nullptr;
+    emu_dyn_smem_ptr() = buf;
+    emu_launch(gx, block, [&] { kernel(args...); }, gy);
+    emu_dyn_smem_ptr() = nullptr;
+    std::free(buf);
+  }
+};
+struct EmuGrid {
+  unsigned x, y;
+  template <typename T, typename = std::enable_if_t<std::is_arithmetic<T>::value>> EmuGrid(T v) : x((unsigned)v), y(1) {}
+  template <typename D, typename = std::enable_if_t<!std::is_arithmetic<D>::value>, typename = void>
+  EmuGrid(const D &d) : x(d.x), y(d.y) {}
+};
+template <typename K> EmuLaunch<K> emu_cfg(K kernel, EmuGrid grid, unsigned block, size_t smem = 0, void * = nullptr) {
+  return EmuLaunch<K>{kernel, grid.x, grid.y, block, smem};
 }
