@@ -88,8 +88,16 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   return *ms = (float)(b->t_ms - a->t_ms), cudaSuccess;
 }
-inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// one process, one address space: the "handle" is the pointer itself
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  std::memset(h, 0, sizeof(*h));
+  std::memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  std::memcpy(p, h.reserved, sizeof(*p));
+  return cudaSuccess;
+}
 inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 
 // ---- device-side odds and ends ----
