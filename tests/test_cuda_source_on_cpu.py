@@ -358,3 +358,24 @@ def test_bench_dbastar_leg_on_the_cpu(emu, monkeypatch):
     out = bench.dbastar_expansions(0)
     assert out["identical_search"] is True and out["expands"] == 12
     assert out["expansions_per_s"] > 0 and len(out["time_search_ms_runs"]) == 5 and out["n_nodes"] > 1
+
+
+@pytest.mark.parametrize("n_prims", [5000, 8300] if FULL else [8300])
+def test_long_rows_on_the_cpu(emu, oracle, golden_dir, n_prims):
+    """Rows beyond the register classes: k_sort_rows' shared-memory network (<= 8192 records) and
+    its global-memory form (longer), on rows FULL of exact distance ties (the library is the shipped
+    one repeated, so equal start states abound and the primitive index decides the order)."""
+    from dynoplan_b200.motions import MotionLibrary
+    p, robot, base, _ = _case(golden_dir, "unicycle1_v0", "bugtrap_0", 100000, 1)
+    reps = -(-n_prims // base.N)
+    lib = MotionLibrary(base.nx, base.nu, np.tile(base.T, reps), np.tile(base.states, (reps, 1)),
+                        np.tile(base.actions, (reps, 1)), np.tile(base.cost, reps)).head(n_prims)
+    nodes = testing.frontier_nodes(robot, lib, 2, p.p_lb, p.p_ub, seed=3)
+    radius = 50.0  # every primitive is a candidate of every node
+    with GpuExpander(robot, p.obstacles, lib) as ex:
+        got = ex.expand(nodes, radius, p.goal, .3, heuristic=0)
+    want = oracle.expand(oracle.OracleModel(robot, p.obstacles), oracle.OracleLibrary(lib), nodes, radius, p.goal, .3, 0)
+    assert np.all(np.diff(got.row_ptr) == n_prims)
+    rep = testing.compare_edges(got, want, robot, radius)
+    assert rep.ok, rep.summary()
+    assert len(np.unique(got.delta_dist)) < got.n_edges // 2  # ties everywhere
