@@ -394,7 +394,9 @@ def small_synthetic(monkeypatch):
     monkeypatch.setattr(testing, "synthetic_case", shrunk)
 
 
-@pytest.mark.parametrize("robot_type", ["unicycle1_v0", "unicycle2_v0", "car1_v0", "quad2d_v0", "acrobot_v0", "quad3d_v0"]
+# (no acrobot: without translation invariance 600 random primitives give the 72 nodes next to no candidates;
+#  the golden vectors and the shipped library above cover it)
+@pytest.mark.parametrize("robot_type", ["unicycle1_v0", "unicycle2_v0", "car1_v0", "quad2d_v0", "quad3d_v0"]
                          if FULL else ["quad3d_v0"])
 def test_gpu_suite_synthetic_library_tests_on_the_cpu(emu, oracle, small_synthetic, robot_type):
     """Device-generated libraries, random box environments: parity with the oracle (12 launches per
