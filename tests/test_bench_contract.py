@@ -57,3 +57,16 @@ def test_reference_arm_line():
     # the headline ratio the driver computes: e2e of our arm / the reference arm
     ours = _line("r1_bench_n1.json")
     assert ours["e2e"]["value"] / d["value"] > 100  # north_star: >= 100x the host-core reference
+
+
+def test_dbastar_leg_failure_is_an_error_object_not_an_exception():
+    """The db-A* leg runs in a child process: with no CUDA device the child exits non-zero (the
+    product has no CPU path) and the parent gets an error object, so the bench line survives."""
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("needs a box without a GPU")
+    sys.path.insert(0, ROOT)
+    import bench
+    out = bench.dbastar_leg(0, timeout_s=120)
+    assert set(out) == {"error", "stderr_tail"} and "no CUDA device" in out["stderr_tail"]
