@@ -7,6 +7,8 @@ mkdir -p $OUT
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
 nproc >> $OUT/gpu.txt
+# first, seconds long and torch-free: smoke() + a toy db-A* search against the oracle (a line per stage)
+timeout 120 python tools/quick_gpu.py $OUT/quick.json > $OUT/quick.log 2>&1; cat $OUT/quick.json
 if [[ " $* " != *" notests "* ]]; then
   timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> $OUT/pytest_gpu.log
