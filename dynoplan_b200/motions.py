@@ -64,6 +64,14 @@ class MotionLibrary:
                              self.actions[s - a:e - b].copy(), self.cost[a:b].copy())
 
     @staticmethod
+    def concat(parts) -> "MotionLibrary":
+        """Libraries back to back (the whole library of a set of shards, in shard order)."""
+        parts = list(parts)
+        return MotionLibrary(parts[0].nx, parts[0].nu, np.concatenate([p.T for p in parts]),
+                             np.concatenate([p.states for p in parts]), np.concatenate([p.actions for p in parts]),
+                             np.concatenate([p.cost for p in parts]))
+
+    @staticmethod
     def from_lists(trajs, nx: int, nu: int, cost=None) -> "MotionLibrary":
         T = np.array([len(t[0]) for t in trajs], dtype=np.int64)
         states = np.concatenate([np.asarray(t[0], dtype=np.float64).reshape(-1, nx) for t in trajs])

@@ -78,11 +78,9 @@ def frontier_nodes(robot: RobotModel, library: MotionLibrary, n_nodes: int, p_lb
     return np.ascontiguousarray(nodes)
 
 
-def synthetic_case(robot_type: str, n_prims: int, n_nodes: int, seed: int = 0,
-                   n_obs: Optional[int] = None, delta: Optional[float] = None,
-                   alpha: float = .5, device: int = 0, library: Optional[MotionLibrary] = None) -> Case:
-    """Synthetic library (GPU generator) + environment + frontier for one robot type."""
-    from .expander import generate_library
+def synthetic_env(robot_type: str, n_obs: Optional[int] = None, seed: int = 0):
+    """(robot, obstacles, p_lb, p_ub) of the synthetic workloads: the quadrotor "window"
+    environment (n_obs None) or random boxes."""
     dim3 = robot_type.startswith("quad3d")
     if dim3 and n_obs is None:
         p_lb, p_ub = WINDOW_ENV["min"], WINDOW_ENV["max"]
@@ -94,8 +92,17 @@ def synthetic_case(robot_type: str, n_prims: int, n_nodes: int, seed: int = 0,
     else:
         p_lb, p_ub = [0.0, 0.0], [6.0, 6.0]
         obstacles = random_box_env(2, 5 if n_obs is None else n_obs, 0, 6, seed)
-    robot = robot_factory(robot_type, p_lb, p_ub)
+    return robot_factory(robot_type, p_lb, p_ub), obstacles, p_lb, p_ub
+
+
+def synthetic_case(robot_type: str, n_prims: int, n_nodes: int, seed: int = 0,
+                   n_obs: Optional[int] = None, delta: Optional[float] = None,
+                   alpha: float = .5, device: int = 0, library: Optional[MotionLibrary] = None) -> Case:
+    """Synthetic library (GPU generator unless one is passed in) + environment + frontier for one
+    robot type."""
+    robot, obstacles, p_lb, p_ub = synthetic_env(robot_type, n_obs, seed)
     if library is None:
+        from .expander import generate_library
         tmin, tmax = DEFAULT_T[robot_type]
         library = generate_library(robot, n_prims, tmin, tmax, seed=seed, device=device)
         if robot.kind == QUAD3D:  # loader normalisation (robots.cpp:3130-3137)
