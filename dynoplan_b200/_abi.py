@@ -107,7 +107,9 @@ class Timings(C.Structure):
                 ("edge_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
                 ("n_edges", C.c_int64), ("n_valid", C.c_int64), ("edge_body_bytes", C.c_int64),
                 ("launches", C.c_int32),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32),
+                ("scatter_ms", C.c_float), ("sort_ms", C.c_float), ("pre_ms", C.c_float),
+                ("sweep_ms", C.c_float), ("tail_ms", C.c_float), ("_pad2", C.c_float)]
 
 
 _lib = None

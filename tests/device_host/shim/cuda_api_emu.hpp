@@ -37,6 +37,9 @@ struct dim3 {
 struct __attribute__((aligned(16))) float4 {
   float x, y, z, w;
 };
+struct __attribute__((aligned(16))) double2 {
+  double x, y;
+};
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 
 inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : "cpu stand-in: call failed"; }
