@@ -123,6 +123,11 @@ inline long long __double_as_longlong(double v) {
   std::memcpy(&r, &v, 8);
   return r;
 }
+inline double __longlong_as_double(long long v) {
+  double r;
+  std::memcpy(&r, &v, 8);
+  return r;
+}
 inline float __double2float_ru(double d) { // round towards +inf
   float f = (float)d;
   return (double)f < d ? std::nextafter(f, INFINITY) : f;
