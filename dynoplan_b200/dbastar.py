@@ -167,7 +167,8 @@ def dbastar(expander: GpuExpander, library: MotionLibrary, start, goal,
                     "edge_checks": str(res.edge_checks), "goal_distance": str(res.goal_distance),
                     "start_distance": str(res.start_distance), "max_jump": str(res.max_jump),
                     "max_collision": str(res.max_collision), "x_bound_distance": str(res.x_bound_distance),
-                    "u_bound_distance": str(res.u_bound_distance), "feasible": str(int(res.feasible))}
+                    "u_bound_distance": str(res.u_bound_distance), "feasible": str(int(res.feasible)),
+                    "cache_evictions": str(res.cache_evictions)}
         out.feasible = bool(res.feasible)
         # traj_out: start / goal, Trajectory::check figures, cost, and -- as the last thing dbastar()
         # does with it -- update_feasibility with the DEFAULT thresholds (dbastar.cpp:1016-1034)

@@ -133,7 +133,11 @@ def _read_trajs(path: str):
         return read_trajectories_boost(path)
     else:
         raise RuntimeError("Incompatible format for motion primitives: " + path)
-    return [(t["states"], t["actions"], t.get("cost", 1e8)) for t in data]
+    # Trajectory::read_from_yaml reads states / actions (/ times) only (motions.cpp:51-75) and the
+    # json / msgpack mapping is NLOHMANN_DEFINE_TYPE_INTRUSIVE(Trajectory, states, actions): a stored
+    # `cost` is ignored, the trajectory keeps its default 1e8 and load_motion_primitives_new assigns
+    # ref_dt * len(actions).  Only the boost archive carries the cost.
+    return [(t["states"], t["actions"], 1e8) for t in data]
 
 
 def load_motion_primitives_new(motions_file: str, robot: RobotModel, max_motions: int = 10 ** 9,

@@ -27,7 +27,9 @@ def test_bin_equals_its_yaml_twin():
         assert s.shape == s2.shape and u.shape == u2.shape and s.shape[0] == u.shape[0] + 1
         # the yaml twin was printed with 6 significant digits
         assert np.allclose(s, s2, rtol=1e-5, atol=1e-6) and np.allclose(u, u2, rtol=1e-5, atol=1e-6)
-        assert abs(c - c2) < 1e-6
+        # only the boost archive carries a cost; the yaml reader ignores a stored one
+        # (Trajectory::read_from_yaml, motions.cpp:51-75): the trajectory keeps its default
+        assert c2 == 1e8 and c < 1e5
 
 
 def test_bin_equals_its_msgpack_twin_bit_for_bit():

@@ -19,9 +19,10 @@ def test_schedule_follows_the_reference():
     assert schedule(o, []) == (.5, 400)
     # solved -> delta * rate, not solved -> delta * .9999; primitives always * rate (size_t truncation)
     d, n = schedule(o, [True])
-    assert d == .5 * .9 and n == 600
+    f32 = np.float32  # Options_dbastar::delta is a float: rounded at every update (idbastar.cpp:132-140)
+    assert d == float(f32(.5 * .9)) and n == 600
     d, n = schedule(o, [True, False])
-    assert d == .5 * .9 * .9999 and n == 900
+    assert d == float(f32(float(f32(.5 * .9)) * .9999)) and n == 900
     assert schedule(Options_idbAStar(num_primitives_0=101, num_primitives_rate=1.5), [False, False])[1] == int(int(101 * 1.5) * 1.5)
     with pytest.raises(NotImplementedError):
         schedule(Options_idbAStar(new_schedule=False), [])
@@ -56,6 +57,46 @@ def test_canonical_pieces_start_at_the_canonical_state(golden_dir, system):
     if robot.offset_dim > ti:  # quad models: canonical velocity is zero too
         v0 = {"quad2d_v0": slice(3, 5), "quadrotor_v0": slice(7, 10)}[system]
         assert np.allclose(back[0, v0], 0)
+
+
+@pytest.mark.parametrize("system", ["unicycle1_v0", "unicycle2_v0", "car1_v0", "quad2d_v0", "quadrotor_v0", "acrobot_v0"])
+def test_canonical_pieces_are_rollouts_like_the_reference(golden_dir, system):
+    """make_trajs_canonical rolls the actions out from canonical_state(x0) (motions.cpp:913-944): a
+    piece with dynamics defects (what an optimiser returns) becomes an exact rollout, a defect-free
+    one is what the closed form gives."""
+    from dynoplan_b200.idbastar import canonical_state
+    from oracle import oracle as orc
+    robot = robot_factory(testing.golden_problem(system, testing.first_env(system)).robotType)
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot, 5, add_noise=False)
+    s, a = lib.primitive(1)
+    rng = np.random.default_rng(0)
+    noisy = s + 1e-3 * rng.normal(size=s.shape)  # defects
+    out = make_traj_canonical(robot, noisy, a)
+    m = orc.OracleModel(robot)
+    x = canonical_state(robot, noisy[0])
+    assert np.array_equal(out[0], x)
+    for k in range(len(a)):
+        x = m.step(x, a[k])
+        assert np.allclose(out[k + 1], x, rtol=0, atol=1e-12), k
+    # the stored primitives are rollouts themselves (to file precision): same as the closed form
+    assert np.allclose(make_traj_canonical(robot, s, a), make_traj_canonical(robot, s), atol=5e-5)
+
+
+def test_ensure_wraps_angles_and_normalises_quaternions():
+    from dynoplan_b200.idbastar import ensure
+    x = np.array([1.0, 2.0, 3.5])
+    ensure(robot_factory("unicycle1_v0", [0, 0], [6, 6]), x)
+    assert abs(x[2] - (3.5 - 2 * np.pi)) < 1e-15
+    c = np.array([0.0, 0.0, -4.0, 7.0])
+    ensure(robot_factory("car1_v0", [0, 0], [6, 6]), c)
+    assert abs(c[2] - (2 * np.pi - 4.0)) < 1e-15 and abs(c[3] - (7.0 - 2 * np.pi)) < 1e-15
+    u2 = np.array([0.0, 0.0, 3.5, 0.0, 0.0])
+    ensure(robot_factory("unicycle2_v0", [0, 0], [6, 6]), u2)  # the base class's no-op
+    assert u2[2] == 3.5
+    q = np.zeros(13)
+    q[3:7] = [0, 0, .6, .9]
+    ensure(robot_factory("quad3d_v0", [-1] * 3, [1] * 3), q)
+    assert abs(np.linalg.norm(q[3:7]) - 1) < 1e-15
 
 
 def test_front_insertion_renumbers(golden_dir):
