@@ -15,6 +15,17 @@ Produces
                                     (dynobench/envs/**/idbastar_v0_db_solution_v0.yaml):
                                     outputs of the REFERENCE ITSELF, used to pin the oracle
   expand_<system>.npz               oracle expansion records for a fixed node batch
+  motions/quadrotor_v0_3000_compact.npz
+                                    the first 3000 quadrotor primitives (what test/dbastar/
+                                    test_dbastar_0.cpp:224-229 searches with) WITHOUT their interior
+                                    states: T, first state, last state, actions.  The reference
+                                    re-rolls a quadrotor primitive out from its (transformed) first
+                                    state (transform_primitive2, robot_models_base.cpp:656-689) and
+                                    reads the stored last state only in the closed-form pre-check, so
+                                    a library whose interior states are that rollout gives the same
+                                    searches as the file (tests/test_quadrotor_instances.py checks it
+                                    against the file where the reference checkout exists); the file's
+                                    13 x 167k full-precision doubles would be 15 MB.
 """
 import glob
 import os
@@ -125,6 +136,26 @@ RAW_TRAJECTORIES = ["unicycle1_v0/parallelpark_0/idbastar_v0_db_solution_v0.yaml
                     "car1_v0/kink_0/idbastar_v0_db_solution_v0.yaml"]
 
 
+def make_quadrotor_compact(n: int = 3000):
+    from dynoplan_b200.motions import load_motion_primitives_new
+    from dynoplan_b200.robots import robot_factory
+    robot = robot_factory("quad3d_v0", [-10] * 3, [10] * 3)
+    lib = load_motion_primitives_new(os.path.join(REF, "dynomotions", SYSTEMS["quadrotor_v0"][0]), robot, n,
+                                     add_noise=False)
+    # undo the loader's quaternion normalisation?  no: it is applied again on load and is idempotent
+    # only to rounding -- so store the RAW file values instead
+    import msgpack as mp
+    with open(os.path.join(REF, "dynomotions", SYSTEMS["quadrotor_v0"][0]), "rb") as f:
+        data = mp.unpackb(f.read(), raw=False)["data"][:n]
+    T = np.array([len(t["states"]) for t in data], dtype=np.int16)
+    first = np.array([t["states"][0] for t in data], dtype=np.float64)
+    last = np.array([t["states"][-1] for t in data], dtype=np.float64)
+    actions = np.concatenate([np.asarray(t["actions"], dtype=np.float64) for t in data])
+    assert np.array_equal(T, lib.T) and actions.shape == lib.actions.shape
+    np.savez_compressed(os.path.join(HERE, "motions", f"quadrotor_v0_{n}_compact.npz"), T=T, first=first, last=last,
+                        actions=actions)
+
+
 def make_expand_fixtures():
     """Oracle expansion records on a fixed node batch per system (golden vectors for the
     oracle itself on CPU and for the CUDA path on the GPU)."""
@@ -161,3 +192,4 @@ def make_expand_fixtures():
 
 if __name__ == "__main__":
     main()
+    make_quadrotor_compact()
