@@ -288,7 +288,12 @@ def dbastar_expansions(device: int):
     want = orc.dbastar(m, orc.OracleLibrary(lib), start, goal, **kw)
     s = want.summary
     same = int(got.data["expands"]) == s["expands"] and np.array_equal(got.motions_used, want.motions_used)
-    return {"workload": f"quadrotor_v0, {n_prims} synthetic primitives, 2 boxes, delta .8, max_expands {max_expands}",
+    try:
+        roadmap = dbastar_roadmap(device)
+    except Exception as e:  # the extra leg must not cost the main one
+        roadmap = {"error": repr(e)}
+    return {"roadmap_heuristic": roadmap,
+            "workload": f"quadrotor_v0, {n_prims} synthetic primitives, 2 boxes, delta .8, max_expands {max_expands}",
             "expands": int(got.data["expands"]), "gpu_calls": int(got.data["gpu_calls"]),
             "nodes_expanded_speculatively": int(got.data["nodes_expanded"]),
             "expansions_per_s": int(got.data["expands"]) / (got.time_search / 1e3),
@@ -296,6 +301,43 @@ def dbastar_expansions(device: int):
             "time_search_ms_runs": [r.time_search for r in runs], "n_nodes": int(got.data["all_nodes"]),
             "cpu_oracle_expansions_per_s": s["expands"] / (s["time_search_ms"] / 1e3),
             "cpu_oracle_time_search_ms": s["time_search_ms"], "identical_search": bool(same)}
+
+
+def dbastar_roadmap(device: int):
+    """db-A* with the roadmap heuristic (Options_dbastar.heuristic = 1, heuristics.cpp:6-44, 177-227)
+    on unicycle1_v0 / bugtrap_0 (test/dbastar/test_dbastar_0.cpp:64-116): map built on the GPU
+    (sample filter + O(n^2) edge test), Heu_roadmap::h per accepted edge on the GPU, against the
+    oracle's search over the same map (identical search, checked) and against heuristic = 0."""
+    from dynoplan_b200 import heuristics, testing
+    from dynoplan_b200.dbastar import Options_dbastar, dbastar
+    from dynoplan_b200.expander import GpuExpander
+    from dynoplan_b200.motions import load_motion_primitives_new
+    from dynoplan_b200.robots import robot_factory
+    from oracle import oracle as orc
+    p = testing.golden_problem("unicycle1_v0", "bugtrap_0")
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    lib = load_motion_primitives_new(os.path.join(testing.GOLDEN, "motions", "unicycle1_v0.msgpack"), robot, 100, rand_seed=1)
+    kw = dict(delta=.3, max_motions=100, search_timelimit=120e3)
+    m = orc.OracleModel(robot, p.obstacles)
+    with GpuExpander(robot, p.obstacles, lib, device=device) as ex:
+        t0 = time.perf_counter()
+        xs, d, _ = heuristics.generate_heuristic_map(ex, robot, p.start, p.goal, num_sample_trials=3000,
+                                                     max_size_heu_map=1000, seed=0)
+        t_map = time.perf_counter() - t0
+        ex.set_heuristic_map(xs, np.minimum(d, 1e300), connect_radius_h=.5)
+        dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, heuristic=1, **kw))  # warm-up
+        got = dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, heuristic=1, **kw))
+        base = dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, heuristic=0, **kw))
+    hm = orc.HeuristicMap(m, xs)
+    hm.attach(.5)
+    want = orc.dbastar(m, orc.OracleLibrary(lib), p.start, p.goal, heuristic=1, **kw)
+    same = int(got.data["expands"]) == want.summary["expands"] and np.array_equal(got.motions_used, want.motions_used)
+    return {"workload": "unicycle1_v0 bugtrap_0, 100 primitives, delta .3, roadmap of %d samples" % len(xs),
+            "map_build_ms": 1e3 * t_map, "solved": bool(got.solved), "cost": float(got.cost),
+            "expands": int(got.data["expands"]), "expands_heuristic0": int(base.data["expands"]),
+            "expansions_per_s": int(got.data["expands"]) / (got.time_search / 1e3),
+            "time_search_ms": got.time_search, "cpu_oracle_time_search_ms": want.summary["time_search_ms"],
+            "identical_search": bool(same)}
 
 
 def dbastar_leg(device: int, timeout_s: float = 300.0):
