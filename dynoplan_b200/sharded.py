@@ -291,6 +291,40 @@ class ShardedExpander:
             x[:, comps] = edges.x_final
         return x
 
+    def final_states_from_nodes(self, edges: Edges, nodes) -> np.ndarray:
+        """Full final states [V, nx] of a fetch WITHOUT x_final (``skip=("x_final",)``): the stored
+        state of every accepted edge (the shards' final-state tables) plus the offset of its node,
+        with the device's own operations -- bit-identical to the x_final rows (the nodes are those
+        of this rank's slice, ``nodes[slice[0]:slice[1]]`` of the expanded batch)."""
+        nodes = np.asarray(nodes, dtype=np.float64).reshape(-1, self.ex.nx)
+        ok = edges.status == 0
+        n_v = edges.chosen_index.shape[0]
+        prim, node = np.empty(n_v, dtype=np.int64), np.empty(n_v, dtype=np.int64)
+        node_of = np.repeat(np.arange(len(edges.row_ptr) - 1), np.diff(edges.row_ptr))
+        prim[edges.valid_slot[ok]] = edges.prim_idx[ok]
+        node[edges.valid_slot[ok]] = node_of[ok]
+        local = prim - self._tab_off[0]
+        ch = edges.chosen_index
+        T = self._tab_T[local]
+        slot = np.full(n_v, 4, dtype=np.int64)
+        for nn in (3, 2, 1, 0):  # first match wins (check_goal, dbastar.cpp:492-512)
+            idx = (np.float32(nn + 1) / np.float32(5.0) * T.astype(np.float32)).astype(np.int32)
+            slot[(ch >= 0) & (idx == ch)] = nn
+        x = self._tab[local, slot].copy()
+        xn = nodes[node]
+        kind = self.ex.robot.kind
+        ti = 0 if kind == 4 else (3 if kind == 5 else 2)
+        if kind in (3, 5):
+            v0 = 7 if kind == 5 else 3
+            t = (np.where(ch >= 0, ch, T - 1).astype(np.float64) * self.ex.robot.ref_dt)[:, None]
+            a = x[:, :ti] + xn[:, :ti]
+            b = t * xn[:, v0:v0 + ti]
+            x[:, :ti] = a + b
+            x[:, v0:v0 + ti] = x[:, v0:v0 + ti] + xn[:, v0:v0 + ti]
+        elif ti:
+            x[:, :ti] = x[:, :ti] + xn[:, :ti]
+        return x
+
     def fetch(self, out: Optional[Edges] = None, skip=(), live: bool = False) -> Edges:
         """Merged records of this rank's node slice on the host (prim_idx are GLOBAL).  With a
         caller-provided ``out`` (e.g. pinned arrays) only the leading entries are written;

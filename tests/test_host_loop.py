@@ -38,6 +38,7 @@ def host_loop(oracle):
     L = C.CDLL(out, mode=C.RTLD_GLOBAL)
     L.mock_create.restype = C.c_void_p
     L.mock_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_int64)]
+    L.mock_set_library.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mock_destroy.argtypes = [C.c_void_p]
     L.mock_set_obstacles.argtypes = [C.c_void_p, C.POINTER(_abi.ObstacleC), C.c_int32]
     L.mock_calls.argtypes = [C.c_void_p]
@@ -62,6 +63,8 @@ def _solve(L, oracle, robot, obstacles, lib, start, goal, heu_map=None, capacity
         hm.attach(heu_map[3])
     T = np.ascontiguousarray(lib.T, dtype=np.int64)
     h = L.mock_create(m._h, ol._h, robot.nx, lib.N, T.ctypes.data_as(C.POINTER(C.c_int64)))
+    L.mock_set_library(h, robot.kind, robot.nu, robot.ref_dt, np.ascontiguousarray(lib.states).ctypes.data_as(C.POINTER(C.c_double)),
+                       np.ascontiguousarray(lib.actions).ctypes.data_as(C.POINTER(C.c_double)))
     env, keep_env = _abi.pack_env(obstacles)
     L.mock_set_obstacles(h, env.obs, env.n_obs)
     if capacity is not None:
@@ -249,6 +252,9 @@ class _MockExpander:
         self.m, self.ol = self.oracle.OracleModel(self.robot, self.obstacles), self.oracle.OracleLibrary(lib)
         self.T = np.ascontiguousarray(lib.T, dtype=np.int64)
         self._h = self.L.mock_create(self.m._h, self.ol._h, self.robot.nx, lib.N, self.T.ctypes.data_as(C.POINTER(C.c_int64)))
+        self.L.mock_set_library(self._h, self.robot.kind, self.robot.nu, self.robot.ref_dt,
+                                np.ascontiguousarray(lib.states).ctypes.data_as(C.POINTER(C.c_double)),
+                                np.ascontiguousarray(lib.actions).ctypes.data_as(C.POINTER(C.c_double)))
         env, self._env_keep = _abi.pack_env(self.obstacles)
         self.L.mock_set_obstacles(self._h, env.obs, env.n_obs)
         self.N = lib.N

@@ -262,6 +262,10 @@ def test_cuda_mailbox_transport_equals_the_unsharded_expansion(robot_type, G):
                 okm = lv.status == 0
                 assert np.array_equal(xs[lv.valid_slot[okm]], full.x_final[e0:e1][okm])
                 assert np.array_equal(lv.prim_idx, got.prim_idx) and np.array_equal(lv.h[lv.valid_slot[okm]], got.h[okm])
+                # ... and no final states at all: recomputed on the host from the slice's node states
+                ln = sx.fetch(skip=("x_final", "delta_dist", "cost_motion"))
+                xs2 = sx.final_states_from_nodes(ln, nodes[sl[q]:sl[q + 1]])
+                assert np.array_equal(xs2[ln.valid_slot[okm]], full.x_final[e0:e1][okm])
             assert n_valid_total == int((full.status == 0).sum())
         # a mailbox region that is too small is an error, not a truncation
         ipc = C.create_string_buffer(64)
