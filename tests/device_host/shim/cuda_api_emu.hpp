@@ -88,6 +88,7 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) {
   return cudaSuccess;
 }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; } // launches are synchronous
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
   return *ms = (float)(b->t_ms - a->t_ms), cudaSuccess;
 }

@@ -38,7 +38,8 @@ def main():
     stream = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(stream)
     results, failed = [], 0
-    for robot_type, n_prims, n_nodes, n_obs in CASES:
+    for k, (robot_type, n_prims, n_nodes, n_obs) in enumerate(CASES):
+        lean = k % 2 == 0  # both mailbox formats: with and without final states
         case = testing.synthetic_case(robot_type, n_prims, n_nodes, seed=11, n_obs=n_obs, device=local)
         sb = sharded.shard_bounds(case.library.N, world)
         shard = case.library.slice(sb[rank], sb[rank + 1])
@@ -50,15 +51,17 @@ def main():
             n0 = ex.expand_count(case.nodes, case.radius, case.goal, case.goal_radius, 0)
             sizes = torch.tensor([n0], device="cuda", dtype=torch.int64)
             dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
-            merger.setup_mailbox(n_nodes, int(2 * int(sizes[0]) / world) + 4096, int(2 * int(sizes[0]) / world) + 4096)
+            merger.setup_mailbox(n_nodes, int(2 * int(sizes[0]) / world) + 4096, int(2 * int(sizes[0]) / world) + 4096,
+                                 lean=lean)
+            merger.gather_final_tables(shard.T)
             par = bench.gather_parity(bench.parity_sharded(mine, merger, case.library, d_nodes, d_goal, local), world)
             torch.cuda.synchronize()
             dist.barrier()
-        par.update(robot=robot_type, n_primitives=n_prims, n_nodes=n_nodes, n_obstacles=len(case.obstacles), gpus=world)
+        par.update(lean_mailbox=lean, robot=robot_type, n_primitives=n_prims, n_nodes=n_nodes, n_obstacles=len(case.obstacles), gpus=world)
         results.append(par)
         failed += par["mismatch"]
         if rank == 0:
-            print(f"{robot_type:13s} G={world} edges={par['edges_compared']:8d} accepted={par['accepted_edges']:8d} "
+            print(f"{robot_type:13s} G={world} lean={int(lean)} edges={par['edges_compared']:8d} accepted={par['accepted_edges']:8d} "
                   f"mismatch={par['mismatch']}  oracle: {par['per_rank'][0]['oracle']}", flush=True)
     if rank == 0 and len(sys.argv) > 1:
         os.makedirs(os.path.dirname(os.path.abspath(sys.argv[1])), exist_ok=True)
