@@ -28,6 +28,7 @@ void *orc_model_create(const ModelDesc *d, int n_obs, const Obstacle *obs) {
   return m;
 }
 void orc_model_destroy(void *m) { delete (Model *)m; }
+void orc_model_set_backward(void *m, int backward) { ((Model *)m)->backward = backward != 0; }
 
 void *orc_library_create(int nx, int nu, int64_t N, const int64_t *T,
                          const double *states, const double *actions,

@@ -162,6 +162,21 @@ void Model::transform_primitive_last_state(const double *p, const double *xs,
   const double *last = xs + (size_t)(T - 1) * d.nx;
   std::memcpy(xout, last, sizeof(double) * d.nx);
   const size_t n_us = (size_t)(T - 1);
+  if (backward && d.kind == QUAD3D) {
+    // transform_primitive_last_state_backward, quadrotor.hpp:175-192:
+    // head<3>() = back().head<3>() + p.head<3>() - (xs.size() - 1) * ref_dt * p.tail<3>()
+    for (int k = 0; k < 3; k++)
+      xout[k] = (last[k] + p[k]) - (double)n_us * d.ref_dt * p[3 + k];
+    for (int k = 0; k < 3; k++)
+      xout[7 + k] = last[7 + k] + p[3 + k];
+    return;
+  }
+  if (backward && d.kind == QUAD2D) {
+    // the planar rotor does not override it: the base class's adds the position offset only
+    // (x_out.head(translation_invariance) += p, robot_models_base.hpp:584-598)
+    xout[0] += p[0], xout[1] += p[1];
+    return;
+  }
   switch (d.kind) {
   case QUAD3D:
     for (int k = 0; k < 3; k++)
@@ -372,6 +387,27 @@ int Model::transform_primitive(const double *p, const double *xs,
                                double *band) const {
   const int nx = d.nx, nu = d.nu;
   int num_valid = T;
+  if (velocity_offset() && backward) {
+    // transform_primitiveDirectReverse on the STORED states (quadrotor.hpp:220-245,
+    // planar_rotor.hpp:226-250), then every state through is_state_valid, last one first
+    // (check_lazy_trajectory, dbastar.cpp:440-445)
+    const int ti = d.kind == QUAD3D ? 3 : 2, v0 = d.kind == QUAD3D ? 7 : 3;
+    for (int i = 0; i < T; i++) {
+      double *o = out + (size_t)i * nx;
+      std::memcpy(o, xs + (size_t)i * nx, sizeof(double) * nx);
+      for (int k = 0; k < ti; k++) {
+        if (d.kind == QUAD3D)
+          o[k] = (xs[(size_t)i * nx + k] + p[k]) - (double)i * d.ref_dt * p[ti + k];
+        else
+          o[k] += p[k] - (double)i * d.ref_dt * p[ti + k];
+        o[v0 + k] += p[ti + k];
+      }
+    }
+    for (int i = T - 1; i >= 0; i--)
+      if (!is_state_valid(out + (size_t)i * nx, band))
+        num_valid = std::min(num_valid, T - 1); // some state is out of bounds: the edge is rejected
+    return num_valid;
+  }
   if (velocity_offset()) {
     transform_state(p, xs, out); // state 0: not bounds-checked (assert only)
     for (int i = 0; i < T - 1; i++) {

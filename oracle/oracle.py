@@ -79,6 +79,7 @@ def lib():
         L.orc_model_create.restype = vp
         L.orc_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(ObstacleC)]
         L.orc_model_destroy.argtypes = [vp]
+        L.orc_model_set_backward.argtypes = [vp, C.c_int]
         L.orc_library_create.restype = vp
         L.orc_library_create.argtypes = [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), dp, dp, dp]
         L.orc_library_destroy.argtypes = [vp]
@@ -160,7 +161,9 @@ class ExpandOut:
 class OracleModel:
     """``Model_robot`` + loaded environment (robot_factory + load_env)."""
 
-    def __init__(self, robot, obstacles=()):
+    def __init__(self, robot, obstacles=(), backward: bool = False):
+        """``backward``: expansions are ``LazyTraj::compute(forward = false)`` over a reverse
+        library (dbastar.hpp:183-214)."""
         d = ModelDesc()
         d.kind, d.nx, d.nu = robot.kind, robot.nx, robot.nu
         d.n_weights = len(robot.distance_weights)
@@ -189,6 +192,8 @@ class OracleModel:
         self.robot = robot
         self.nx, self.nu = robot.nx, robot.nu
         self._h = lib().orc_model_create(C.byref(d), len(obstacles), obs)
+        if backward:
+            lib().orc_model_set_backward(self._h, 1)
 
     def __del__(self):
         if getattr(self, "_h", None):
