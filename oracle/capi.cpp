@@ -120,7 +120,10 @@ void *orc_expand(void *m_, void *l_, int64_t n_use, int B, const double *nodes,
         break;
       const double *x = nodes + (size_t)b * nx;
       m->canonical_state(x, canonical);
-      nearest_r(*m, *l, n_use, canonical, radius, nb[b], (filter_only & 2) != 0);
+      if (filter_only & 4) // the k-d index (kdindex.cpp): same result, sub-linear like nigh's tree
+        nearest_r_kd(*m, *l, n_use, canonical, radius, nb[b]);
+      else
+        nearest_r(*m, *l, n_use, canonical, radius, nb[b], (filter_only & 2) != 0);
       if (filter_only & 1)
         continue;
       er[b].reserve(nb[b].size());
@@ -131,6 +134,14 @@ void *orc_expand(void *m_, void *l_, int64_t n_use, int B, const double *nodes,
     if (e)
       err.store(e);
   };
+  if (filter_only & 4) { // build the index once, before the threads ask for it
+    std::vector<std::pair<double, int64_t>> tmp;
+    double c0[MAX_NX];
+    if (B > 0) {
+      m->canonical_state(nodes, c0);
+      nearest_r_kd(*m, *l, n_use, c0, 0.0, tmp);
+    }
+  }
   if (n_threads <= 1) {
     work();
   } else {
