@@ -12,3 +12,6 @@ print(f"value {d['value']:.4g}  ms/step {d['ms_per_step']:.4f}  e2e ms {d['e2e']
       f"parity {d.get('parity', {}).get('mismatch')}  cpu {d['cpu_baseline']['value']:.3g}")
 if "dbastar" in d:
     print("dbastar:", {k: d["dbastar"].get(k) for k in ("expansions_per_s", "time_search_ms", "time_gpu_ms", "identical_search", "error")})
+    for leg in ("quadrotor_window", "roadmap_heuristic"):
+        w = d["dbastar"].get(leg) or {}
+        print(" ", leg, {k: w.get(k) for k in ("expands", "expansions_per_s", "time_search_ms", "cpu_oracle_time_search_ms", "identical_search", "error")})
