@@ -27,8 +27,10 @@ def test_oracle_reproduces_stored_reference_solution(oracle, golden_dir, system,
     n_prims, delta, extra = CFG[system]
     p = testing.golden_problem(system, env)
     robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    # rand_seed: the loader's 1e-7 noise comes from the process-global rand() stream, which other
+    # tests advance -- a fresh reference process starts at srand(1)
     lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"),
-                                     robot, n_prims)
+                                     robot, n_prims, rand_seed=1)
     m = oracle.OracleModel(robot, p.obstacles)
     out = oracle.dbastar(m, oracle.OracleLibrary(lib), p.start, p.goal, delta=delta,
                          max_motions=n_prims, search_timelimit=120e3, **extra)
@@ -43,7 +45,8 @@ def test_oracle_reproduces_stored_reference_solution(oracle, golden_dir, system,
     assert np.max(np.abs(out.states - want)) < 1e-5 * (1 + np.abs(want).max())
     assert np.max(np.abs(out.actions - np.array(ref["actions"], dtype=float))) < 1e-5
     for key in ("max_jump", "goal_distance", "start_distance"):
-        assert abs(s[key] - ref[key]) < 2e-6, key
+        # 6 significant digits in the file (half a unit of the last one) + the loader noise along the plan
+        assert abs(s[key] - ref[key]) < 6e-6, key
     assert s["max_collision"] == ref["max_collision"] == 0
 
 

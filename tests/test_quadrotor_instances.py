@@ -22,9 +22,16 @@ INSTANCES = {"window": (3000, 8270, 2.54), "recovery": (3000, 7711, 3.46), "reco
 KW = dict(delta=.8, limit_branching_factor=30, search_timelimit=600e3)
 
 
+_CACHE = {}
+
+
 def _library(golden_dir, robot, n):
-    return testing.load_compact_library(os.path.join(golden_dir, "motions", "quadrotor_v0_3000_compact.npz"), robot, n,
-                                        rand_seed=1)
+    """The first n primitives (loaded once per session: the noise of primitive i does not depend on
+    how many follow it, so the head of the 3000 is the library a load of n gives)."""
+    if "lib" not in _CACHE:
+        _CACHE["lib"] = testing.load_compact_library(os.path.join(golden_dir, "motions", "quadrotor_v0_3000_compact.npz"),
+                                                     robot, 3000, rand_seed=1)
+    return _CACHE["lib"].head(n)
 
 
 def test_compact_library_is_the_reference_file(oracle, golden_dir):
