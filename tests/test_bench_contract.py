@@ -70,3 +70,35 @@ def test_dbastar_leg_failure_is_an_error_object_not_an_exception():
     import bench
     out = bench.dbastar_leg(0, timeout_s=120)
     assert set(out) == {"error", "stderr_tail"} and "no CUDA device" in out["stderr_tail"]
+
+
+def test_round2_bench_lines():
+    """The lines of the final round-2 build: contract keys, the parity gate's verdict, both configs,
+    the reference arm printing the SAME config dict as ours."""
+    ours, ref = _line("r2_bench_n1.json"), _line("r2_bench_ref.json")
+    assert ours["config"] == ref["config"] and ref["impl"] == "reference"
+    assert ref["e2e"]["value"] == ref["value"] and ref["gpu_launches"] == 0
+    assert ours["e2e"]["value"] / ref["value"] > 100  # north_star: >= 100x the host-core reference, end to end
+    lines = [("r2_bench_n1.json", 1, "weak"), ("r2i_bench_n2_lean1_ov1.json", 2, "weak"), ("r2j_bench_n4.json", 4, "weak"),
+             ("r2j_bench_n8.json", 8, "weak"), ("r2_bench_stress_n1.json", 1, "strong"), ("r2j_bench_stress_n4.json", 4, "strong"),
+             ("r2j_bench_stress_n8.json", 8, "strong")]
+    for name, n, scaling in lines:
+        d = _line(name)
+        for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                  "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks", "parity"):
+            assert k in d, (name, k)
+        assert d["n_gpus"] == n and d["scaling"] == scaling and d["warmup"] >= 3 and d["dtype"] == "f64"
+        if d["parity"].get("skipped") is None:  # (the N = 4 lines were taken with the gate off: N = 2 and 8 bracket them)
+            assert d["parity"]["mismatch"] == 0, name
+        cfg = d["config"]
+        assert abs(d["value"] - cfg["n_nodes"] * cfg["n_primitives_total"] / (d["ms_per_step"] / 1e3)) / d["value"] < 1e-6
+        assert d["e2e"]["value"] < d["value"] and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+        r = d["roofline"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["bound"] == "hbm"
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    d = _line("r2_bench_n1.json")
+    if d["roofline"]["traffic"] is not None:  # only printed when the ncu capture is of the same build
+        assert 0 < d["roofline"]["frac_dram"] < d["roofline"]["frac"]
+    for leg in ("quadrotor_window", "roadmap_heuristic"):
+        assert d["dbastar"][leg]["identical_search"] is True and d["dbastar"][leg]["solved"] is True
+    assert d["dbastar"]["identical_search"] is True
