@@ -301,8 +301,21 @@ def dbastar_expansions(device: int):
     with GpuExpander(robot, obstacles, lib, device=device) as ex:
         dbastar(ex, lib, start, goal, Options_dbastar(fix_seed=True, **kw))  # warm-up (pinned buffers)
         runs = [dbastar(ex, lib, start, goal, Options_dbastar(fix_seed=True, **kw)) for _ in range(5)]
+        # T_n's snapshot queries on the device: the default (-1) switches them on once
+        # T_n holds 4096 nodes; both fixed settings next to it, same search each time
+        tn = {}
+        for name, mode in (("host_only", 0), ("device_from_the_start", 1)):
+            rs = sorted((dbastar(ex, lib, start, goal, Options_dbastar(fix_seed=True, tn_device=mode, **kw))
+                         for _ in range(3)), key=lambda r: r.time_search)
+            tn[name] = {"time_search_ms": rs[1].time_search, "time_gpu_ms": float(rs[1].data["time_gpu"]),
+                        "device_rows": int(rs[1].data["tn_device_rows"]), "host_rows": int(rs[1].data["tn_host_rows"]),
+                        "same_search": rs[1].data["expands"] == runs[0].data["expands"]
+                        and np.array_equal(rs[1].motions_used, runs[0].motions_used)
+                        and rs[1].data["all_nodes"] == runs[0].data["all_nodes"]}
     runs.sort(key=lambda r: r.time_search)
     got = runs[len(runs) // 2]  # the median search of five identical ones (a 15 ms measurement is noisy)
+    tn["default"] = {"time_search_ms": got.time_search, "device_rows": int(got.data["tn_device_rows"]),
+                     "host_rows": int(got.data["tn_host_rows"])}
     m = orc.OracleModel(robot, obstacles)
     want = orc.dbastar(m, orc.OracleLibrary(lib), start, goal, **kw)
     s = want.summary
@@ -315,7 +328,7 @@ def dbastar_expansions(device: int):
         window = dbastar_window(device)
     except Exception as e:
         window = {"error": repr(e)}
-    return {"roadmap_heuristic": roadmap, "quadrotor_window": window,
+    return {"roadmap_heuristic": roadmap, "quadrotor_window": window, "tn_device": tn,
             "workload": f"quadrotor_v0, {n_prims} synthetic primitives, 2 boxes, delta .8, max_expands {max_expands}",
             "expands": int(got.data["expands"]), "gpu_calls": int(got.data["gpu_calls"]),
             "nodes_expanded_speculatively": int(got.data["nodes_expanded"]),
