@@ -206,6 +206,12 @@ void *orc_dbastar(void *m_, void *l_, const double *start, const double *goal,
   *r = dbastar(*(Model *)m_, *(Library *)l_, start, goal, *opt);
   return r;
 }
+void *orc_tdbastar(void *m_, void *l_, const double *start, const double *goal, const SearchOptions *opt,
+                   int rewire, const TimedConstraint *constraints, int n_constraints) {
+  SearchResult *r = new SearchResult();
+  *r = tdbastar(*(Model *)m_, *(Library *)l_, start, goal, *opt, rewire != 0, constraints, n_constraints);
+  return r;
+}
 struct SearchSummary {
   int32_t status, solved, feasible, err;
   double cost;

@@ -498,10 +498,18 @@ SearchResult dbastar(const Model &m, const Library &lib, const double *start,
     const double *us = lib.us(prim);
     res.actions.insert(res.actions.end(), us, us + take_num_actions * nu);
   }
+  res.cost = (nu ? res.actions.size() / nu : 0) * m.d.ref_dt; // :1019
+  check_plan(m, start, goal, opt.delta, &res);
+  return res;
+}
+
+// Trajectory::check (dynobench/src/motions.cpp:172-225) of res->states / res->actions, then
+// update_feasibility with the thresholds of dbastar.cpp:1023-1029 (= tdbastar.cpp:960-967)
+void check_plan(const Model &m, const double *start, const double *goal, double delta, SearchResult *res_) {
+  SearchResult &res = *res_;
+  const int nx = m.d.nx, nu = m.d.nu;
   const size_t n_states = res.states.size() / nx;
   const size_t n_actions = nu ? res.actions.size() / nu : 0;
-  res.cost = n_actions * m.d.ref_dt; // :1019
-
   // Trajectory::check (dynobench/src/motions.cpp:172-225) with verbose = true
   for (size_t i = 0; i < n_states; i++) { // check_cols :430-452
     double dd = m.collision_distance(res.states.data() + i * nx);
@@ -537,10 +545,9 @@ SearchResult dbastar(const Model &m, const Library &lib, const double *start,
     res.start_distance = m.distance(res.states.data(), start, &res.err);
   }
   // update_feasibility with the thresholds of dbastar.cpp:1023-1029
-  res.feasible = res.max_jump < opt.delta && res.goal_distance < opt.delta &&
-                 res.start_distance < opt.delta && res.max_collision < 5e-2 &&
+  res.feasible = res.max_jump < delta && res.goal_distance < delta &&
+                 res.start_distance < delta && res.max_collision < 5e-2 &&
                  res.x_bound_distance < 1e-2 && res.u_bound_distance < 1e-2;
-  return res;
 }
 
 } // namespace orc
