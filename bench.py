@@ -328,7 +328,11 @@ def dbastar_expansions(device: int):
         window = dbastar_window(device)
     except Exception as e:
         window = {"error": repr(e)}
-    return {"roadmap_heuristic": roadmap, "quadrotor_window": window, "tn_device": tn,
+    try:
+        tdb = tdbastar_leg(device)
+    except Exception as e:
+        tdb = {"error": repr(e)}
+    return {"roadmap_heuristic": roadmap, "quadrotor_window": window, "tn_device": tn, "tdbastar": tdb,
             "workload": f"quadrotor_v0, {n_prims} synthetic primitives, 2 boxes, delta .8, max_expands {max_expands}",
             "expands": int(got.data["expands"]), "gpu_calls": int(got.data["gpu_calls"]),
             "nodes_expanded_speculatively": int(got.data["nodes_expanded"]),
@@ -406,6 +410,34 @@ def dbastar_window(device: int):
             "time_gpu_ms": float(got.data["time_gpu"]),
             "cpu_oracle_expansions_per_s": s["expands"] / (s["time_search_ms"] / 1e3),
             "cpu_oracle_time_search_ms": s["time_search_ms"], "identical_search": bool(same)}
+
+
+def tdbastar_leg(device: int):
+    """tdb-A* (src/tdbastar/tdbastar.cpp) on the car-with-trailer problem of the reference's own test
+    (test/tdbastar/test_tdbastar_0.cpp:150-231: swap1_trailer, 400 primitives, delta .75, the 12 constraints
+    of envs/car1_v0/constraints/constraints_trailer.yaml) against the oracle's restatement (identical
+    search, checked)."""
+    from dynoplan_b200 import testing
+    from dynoplan_b200.expander import GpuExpander
+    from dynoplan_b200.motions import load_motion_primitives_new
+    from dynoplan_b200.robots import robot_factory
+    from dynoplan_b200.tdbastar import Options_tdbastar, constraints_from_yaml, tdbastar
+    from oracle import oracle as orc
+    robot = robot_factory("car1_v0", [0, 0], [5, 5])
+    start, goal = [1, 2.5, 0, 0], [4, 2.5, 0, 0]
+    lib = load_motion_primitives_new(os.path.join(testing.GOLDEN, "motions", "car1_v0.msgpack"), robot, 400, rand_seed=1)
+    cons = constraints_from_yaml(os.path.join(testing.GOLDEN, "constraints", "car1_v0.yaml"))
+    kw = dict(delta=.75, max_motions=400, search_timelimit=120e3)
+    with GpuExpander(robot, [], lib, device=device) as ex:
+        tdbastar(ex, lib, start, goal, Options_tdbastar(fix_seed=True, rewire=False, **kw), cons)  # warm-up
+        got = tdbastar(ex, lib, start, goal, Options_tdbastar(fix_seed=True, rewire=False, **kw), cons)
+    want = orc.tdbastar(orc.OracleModel(robot, []), orc.OracleLibrary(lib), start, goal,
+                        constraints=[(c.time, c.constrained_state) for c in cons], rewire=False, **kw)
+    same = int(got.data["expands"]) == want.summary["expands"] and np.array_equal(got.motions_used, want.motions_used)
+    return {"workload": "car1_v0 swap1_trailer, 400 primitives, delta .75, 12 (time, state) constraints, rewire off",
+            "solved": bool(got.solved), "cost": float(got.cost), "expands": int(got.data["expands"]),
+            "time_search_ms": got.time_search, "cpu_oracle_time_search_ms": want.summary["time_search_ms"],
+            "identical_search": bool(same)}
 
 
 def dbastar_leg(device: int, timeout_s: float = 300.0):
