@@ -47,7 +47,7 @@ static double so2_interpolation(double from, double to, double t) {
 
 // unicycle1.cpp:155-168, unicycle2.cpp:170-185, car.cpp:288-304, planar_rotor.cpp:168-184,
 // acrobot.cpp:366-381, quadrotor.cpp:389-408 (Eigen slerp, Quaternion.h)
-static void interpolate(const Model &m, double *xt, const double *a, const double *b, double t) {
+void interpolate(const Model &m, double *xt, const double *a, const double *b, double t) {
   const int nx = m.d.nx;
   for (int k = 0; k < nx; k++)
     xt[k] = a[k] + t * (b[k] - a[k]);
