@@ -212,6 +212,11 @@ void *orc_tdbastar(void *m_, void *l_, const double *start, const double *goal, 
   *r = tdbastar(*(Model *)m_, *(Library *)l_, start, goal, *opt, rewire != 0, constraints, n_constraints);
   return r;
 }
+void *orc_dbrrt(void *m, void *lib, const double *start, const double *goal, const RrtOptions *opt) {
+  SearchResult *r = new SearchResult();
+  *r = dbrrt(*(Model *)m, *(Library *)lib, start, goal, *opt);
+  return r;
+}
 void *orc_dbrrt_connect(void *m_fwd, void *m_bwd, void *lib, void *lib_rev, const double *start, const double *goal,
                         const RrtOptions *opt) {
   SearchResult *r = new SearchResult();

@@ -399,6 +399,40 @@ class RrtOptions(C.Structure):  # orc::RrtOptions (Options_dbrrt, dbrrt.hpp:11-4
                 ("choose_first_motion_valid", C.c_int)]
 
 
+def _rrt_options(opts) -> "RrtOptions":
+    o = RrtOptions(delta=.3, goal_region=.3, goal_bias=.1, prob_expand_forward=.5, max_step_size=3., cost_jump=1.,
+                   timelimit=1e4, max_expands=10000, max_motions=1000, seed=-1, choose_first_motion_valid=1)
+    for k, v in opts.items():
+        if not hasattr(o, k):
+            raise TypeError("unknown option " + k)
+        setattr(o, k, v)
+    return o
+
+
+def _search_out(L, r, model) -> SearchOut:
+    try:
+        s = SearchSummary()
+        L.orc_dbastar_summary(r, C.byref(s))
+        states = np.zeros((s.n_states, model.nx))
+        actions = np.zeros((s.n_actions, model.nu))
+        mu = np.zeros(s.n_motions, np.int64)
+        im = np.zeros(s.n_motions, np.int32)
+        L.orc_dbastar_copy(r, _dp(states), _dp(actions), mu.ctypes.data_as(C.POINTER(C.c_int64)),
+                           im.ctypes.data_as(C.POINTER(C.c_int32)))
+        return SearchOut({f[0]: getattr(s, f[0]) for f in SearchSummary._fields_}, states, actions, mu, im)
+    finally:
+        L.orc_dbastar_free(r)
+
+
+def dbrrt(model: OracleModel, olib: OracleLibrary, start, goal, **opts) -> SearchOut:
+    """Unidirectional db-RRT, ``dbrrt()`` (src/dbrrt/dbrrt.cpp:920-1652) without AO / optimisation."""
+    o = _rrt_options(opts)
+    L = lib()
+    L.orc_dbrrt.restype = C.c_void_p
+    L.orc_dbrrt.argtypes = [C.c_void_p] * 2 + [C.POINTER(C.c_double)] * 2 + [C.POINTER(RrtOptions)]
+    return _search_out(L, L.orc_dbrrt(model._h, olib._h, _dp(_vec(start)), _dp(_vec(goal)), C.byref(o)), model)
+
+
 def dbrrt_connect(model_fwd: OracleModel, model_bwd: OracleModel, olib: OracleLibrary, olib_rev: OracleLibrary,
                   start, goal, **opts) -> SearchOut:
     """dbrrtConnect (src/dbrrt/dbrrt.cpp:342-913); ``model_bwd`` = the same robot with ``backward=True``,

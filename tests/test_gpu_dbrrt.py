@@ -39,3 +39,25 @@ def test_gpu_dbrrt_connect_equals_the_oracle(oracle, golden_dir, system, env, n_
     assert abs(got.cost - s["cost"]) < 1e-4 and np.max(np.abs(got.states - want.states)) < 1e-9
     print(system, env, "expands", got.data["expands"], "nodes", got.data["all_nodes"], "search ms %.1f" % got.time_search,
           "of which GPU %.1f" % float(got.data["time_gpu"]), "oracle ms %.1f" % s["time_search_ms"])
+
+
+@pytest.mark.parametrize("system,env,n_prims,delta,goal_region", [("unicycle1_v0", "bugtrap_0", 30, .3, .3),
+                                                                   ("unicycle2_v0", "parallelpark_0", 200, .5, .5),
+                                                                   ("quadrotor_v0", "recovery", 400, .8, .8)])
+def test_gpu_dbrrt_equals_the_oracle(oracle, golden_dir, system, env, n_prims, delta, goal_region):
+    """The unidirectional variant (dbrrt(), src/dbrrt/dbrrt.cpp:920-1652, no AO / optimisation)."""
+    from dynoplan_b200.dbrrt import Options_dbrrt, dbrrt
+    from dynoplan_b200.expander import GpuExpander
+    from dynoplan_b200.motions import load_motion_primitives_new
+    p = testing.golden_problem(system, env)
+    robot = robot_factory(p.robotType, p.p_lb, p.p_ub)
+    lib = load_motion_primitives_new(os.path.join(golden_dir, "motions", system + ".msgpack"), robot, n_prims, rand_seed=1)
+    kw = dict(delta=delta, goal_region=goal_region, seed=0, max_expands=100000)
+    want = oracle.dbrrt(oracle.OracleModel(robot, p.obstacles), oracle.OracleLibrary(lib), p.start, p.goal, timelimit=3e5, **kw)
+    with GpuExpander(robot, p.obstacles, lib) as ex:
+        got = dbrrt(ex, lib, p.start, p.goal, Options_dbrrt(timelimit=3e5, **kw))
+    s = want.summary
+    assert got.solved_raw and s["solved"] == 1 and got.feasible
+    assert int(got.data["expands"]) == s["expands"] and int(got.data["all_nodes"]) == s["n_nodes"]
+    assert np.array_equal(got.motions_used, want.motions_used) and np.array_equal(got.actions, want.actions)
+    assert abs(got.cost - s["cost"]) < 1e-4 and np.max(np.abs(got.states - want.states)) < 1e-9
