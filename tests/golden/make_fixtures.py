@@ -125,6 +125,14 @@ def main():
     os.makedirs(os.path.join(HERE, "trajectories"), exist_ok=True)
     for rel in RAW_TRAJECTORIES:
         shutil.copy(REF + "dynobench/envs/" + rel, os.path.join(HERE, "trajectories", rel.replace("/", "__")))
+    # the constraint files of the reference's tdb-A* tests (test/tdbastar/test_tdbastar_0.cpp:150-231), verbatim;
+    # their problems (envs/*/swap/swap1_*.yaml: empty [0, 5]^2, start (1, 2.5, 0..), goal (4, 2.5, 0..)) are
+    # spelled out in the tests
+    os.makedirs(os.path.join(HERE, "constraints"), exist_ok=True)
+    for src, dst in (("unicycle1_v0/constraints/constraints_unicycle.yaml", "unicycle1_v0.yaml"),
+                     ("unicycle2_v0/constraints/constraints_unicycle2.yaml", "unicycle2_v0.yaml"),
+                     ("car1_v0/constraints/constraints_trailer.yaml", "car1_v0.yaml")):
+        shutil.copy(REF + "dynobench/envs/" + src, os.path.join(HERE, "constraints", dst))
     make_expand_fixtures()
 
 
