@@ -22,15 +22,15 @@ from typing import Optional
 import numpy as np
 
 from . import _abi
-from .dbastar import TERMINATE_STATUS
+from .dbastar import TERMINATE_STATUS, _YamlOptions
 from .expander import GpuExpander
 from .motions import MotionLibrary, reverse_motions
 
 
 @dataclass
-class Options_dbrrt:
-    """``Options_dbrrt`` (dbrrt.hpp:11-48): the fields ``dbrrtConnect`` reads, with its defaults."""
-    use_connect: bool = True
+class Options_dbrrt(_YamlOptions):
+    """``Options_dbrrt`` (dbrrt.hpp:11-48) with its defaults, ``read_from_yaml`` and ``print``."""
+    use_connect: bool = False
     prob_expand_forward: float = .5
     seed: int = -1
     cost_jump: float = 1.0
@@ -43,6 +43,29 @@ class Options_dbrrt:
     timelimit: float = 10000.0  # ms
     max_motions: int = 1000
     do_optimization: bool = False
+    # parsed by the reference; read only by the variants that are not built (AO-db-RRT, optimisation) or never
+    extract_primitives: bool = False
+    add_to_search_tree: bool = False
+    best_cost_prune_factor: float = .9
+    cost_weight: float = .01
+    ao_rrt: bool = False
+    ao_rrt_rebuild_tree: bool = True
+    cost_bound: float = 200.0
+    debug: bool = False
+    new_invariance: bool = True
+    use_nigh_nn: bool = True
+    motionsFile: str = ""
+    cut_actions: bool = False
+    check_cols: bool = True
+    use_collision_shape: bool = False
+    # Options_dbrrt::__load_data (dbrrt.hpp:50-87): keys and their order (goal_bias is not among them); the
+    # reference looks the options up under "options_dbastar" (dbrrt.hpp:101-107)
+    yaml_key = "options_dbastar"
+    yaml_fields = ("do_optimization", "cost_jump", "best_cost_prune_factor", "cost_weight", "cost_bound",
+                   "ao_rrt_rebuild_tree", "ao_rrt", "use_connect", "prob_expand_forward", "add_to_search_tree",
+                   "extract_primitives", "max_step_size", "choose_first_motion_valid", "goal_region", "debug",
+                   "new_invariance", "timelimit", "max_expands", "delta", "max_motions", "use_nigh_nn", "seed",
+                   "motionsFile", "cut_actions", "check_cols", "use_collision_shape")
 
 
 @dataclass
@@ -88,8 +111,8 @@ def _info_out(res, robot) -> "Info_out_dbrrt":
 def dbrrt(expander: GpuExpander, library: MotionLibrary, start, goal, options: Optional[Options_dbrrt] = None) -> Info_out_dbrrt:
     """Unidirectional db-RRT (``dbrrt()``, src/dbrrt/dbrrt.cpp:920-1652, ``ao_rrt`` and ``do_optimization`` off)."""
     o = options or Options_dbrrt()
-    if o.do_optimization:
-        raise NotImplementedError("db-RRT: the trajectory-optimisation step is out of scope (module docstring)")
+    if o.do_optimization or o.ao_rrt:
+        raise NotImplementedError("db-RRT: the optimisation step and AO-db-RRT are out of scope (module docstring)")
     L = _abi.lib()
     ro = _options_c(o)
     md = _abi.pack_model(expander.robot)

@@ -28,7 +28,8 @@ from .motions import MotionLibrary
 
 @dataclass
 class Options_tdbastar(Options_dbastar):
-    """``Options_tdbastar`` = the db-A* options + ``rewire`` (options.hpp:57)."""
+    """``Options_tdbastar`` = the db-A* options + ``rewire`` (options.hpp:57).  The yaml keys are the db-A*
+    ones (src/tdbastar/options.cpp:16-41: ``rewire`` is not loadable in the reference either)."""
     rewire: bool = True
     yaml_key = "options_tdbastar"
 
