@@ -398,8 +398,6 @@ def dbastar_window(device: int):
     with GpuExpander(robot, p.obstacles, lib, device=device) as ex:
         dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, **kw))  # warm-up
         runs = [dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, **kw)) for _ in range(3)]
-        sync = sorted((dbastar(ex, lib, p.start, p.goal, Options_dbastar(fix_seed=True, prefetch=False, **kw))
-                       for _ in range(3)), key=lambda r: r.time_search)[1]
     runs.sort(key=lambda r: r.time_search)
     got = runs[1]
     want = orc.dbastar(orc.OracleModel(robot, p.obstacles), orc.OracleLibrary(lib), p.start, p.goal, **kw)
@@ -409,11 +407,7 @@ def dbastar_window(device: int):
                         "solved to completion", "solved": bool(got.solved), "cost": float(got.cost),
             "expands": int(got.data["expands"]), "gpu_calls": int(got.data["gpu_calls"]),
             "expansions_per_s": int(got.data["expands"]) / (got.time_search / 1e3), "time_search_ms": got.time_search,
-            "time_gpu_ms": float(got.data["time_gpu"]), "prefetch_calls": int(got.data["prefetch_calls"]),
-            "without_prefetch": {"time_search_ms": sync.time_search, "time_gpu_ms": float(sync.data["time_gpu"]),
-                                 "gpu_calls": int(sync.data["gpu_calls"]),
-                                 "same_search": sync.data["expands"] == got.data["expands"]
-                                 and np.array_equal(sync.motions_used, got.motions_used)},
+            "time_gpu_ms": float(got.data["time_gpu"]),
             "cpu_oracle_expansions_per_s": s["expands"] / (s["time_search_ms"] / 1e3),
             "cpu_oracle_time_search_ms": s["time_search_ms"], "identical_search": bool(same)}
 

@@ -72,7 +72,6 @@ class Options_dbastar(_YamlOptions):
     max_batch: int = 256  # ours: open nodes expanded per GPU call
     tn_device: int = -1  # ours: T_n snapshot queries on the device (0 off, 1 on, -1 once T_n is large)
     tn_device_min: int = 4096
-    prefetch: bool = True  # ours: speculative batches issued asynchronously, ahead of the miss
     # Options_dbastar::__load_data (src/dbastar/options.cpp:16-42): keys and their order
     yaml_key = "options_dbastar"
     yaml_fields = ("fix_seed", "new_invariance", "connect_radius_h", "use_collision_shape", "delta", "alpha",
@@ -144,7 +143,6 @@ def dbastar(expander: GpuExpander, library: MotionLibrary, start, goal,
     so.max_expands, so.limit_branching_factor = o.max_expands, o.limit_branching_factor
     so.search_timelimit, so.max_batch = o.search_timelimit, o.max_batch
     so.tn_device, so.tn_device_min = o.tn_device, o.tn_device_min
-    so.prefetch = int(bool(o.prefetch))
     md = _abi.pack_model(expander.robot)
     lc, keep = _abi.pack_library(library)
     start = np.ascontiguousarray(np.asarray(start, dtype=np.float64))
@@ -174,7 +172,7 @@ def dbastar(expander: GpuExpander, library: MotionLibrary, start, goal,
                     "max_collision": str(res.max_collision), "x_bound_distance": str(res.x_bound_distance),
                     "u_bound_distance": str(res.u_bound_distance), "feasible": str(int(res.feasible)),
                     "cache_evictions": str(res.cache_evictions), "tn_device_rows": str(res.tn_device_rows),
-                    "tn_host_rows": str(res.tn_host_rows), "prefetch_calls": str(res.prefetch_calls)}
+                    "tn_host_rows": str(res.tn_host_rows)}
         out.feasible = bool(res.feasible)
         # traj_out: start / goal, Trajectory::check figures, cost, and -- as the last thing dbastar()
         # does with it -- update_feasibility with the DEFAULT thresholds (dbastar.cpp:1016-1034)
